@@ -1,0 +1,26 @@
+"""Shared description of the committed golden fixtures (tests/golden/*.npz).
+
+The fixtures were produced by oracle/gen_golden.py, i.e. by the reference's own Python
+drivers running on the C restatement of its Fortran kernels.  Keep in sync with CASES there.
+"""
+import numpy as np
+
+CASES = {
+    # name: (modelname, geometry, (nx,ny,nz), (Lx,Ly,Lz), extras, nsteps)
+    "les_closed": ("LES", "closed", (16, 8, 8), (4.0, 2.0, 2.0), {}, 4),
+    "les_perio_xy_rot": ("LES", "perio_xy", (8, 8, 16), (1.0, 1.0, 2.0), {"rotating": True, "coriolis": 3.0}, 3),
+    "euler_perio_xyz": ("Euler3d", "perio_xyz", (8, 8, 8), (2 * np.pi,) * 3, {"dt_max": 1.0}, 4),
+    "les_closed_rk3": ("LES", "closed", (8, 16, 8), (1.0, 2.0, 1.0), {"timestepping": "RK3_SSP"}, 2),
+    "les_closed_ef_diff": ("LES", "closed", (8, 8, 8), (1.0, 1.0, 1.0),
+                           {"timestepping": "EF", "diff_coef": {"u": 1e-3, "b": 2e-3}}, 3),
+}
+
+SCALARS = ("b", "p", "ke", "div")
+VECTORS = ("u", "U", "vor")
+
+
+def flat_param(name):
+    modelname, geometry, (nx, ny, nz), (Lx, Ly, Lz), extra, nsteps = CASES[name]
+    kw = dict(modelname=modelname, cfl=0.8, dt_max=0.05)
+    kw.update(extra)
+    return dict(nx=nx, ny=ny, nz=nz, geometry=geometry, Lx=Lx, Ly=Ly, Lz=Lz, **kw), nsteps
