@@ -1,0 +1,174 @@
+/*
+ * nyles_b200.h -- C ABI of libnyles_b200.so
+ *
+ * B200 (sm_100a) replacement for the two native layers under Nyles' LES time step:
+ *   (1) the f2py Fortran kernels  core/fortran_{vorticity,vortex_force,upwind,kinenergy,
+ *       bernoulli}.f90 + core/weno.f90          (reference interface: core/Makefile:1-2)
+ *   (2) the ctypes-loaded multigrid library libmgmod64.so built from core/mgfor/*.f90
+ *       (reference interface: core/mgfordriver.py:14-24, core/build.py:107-121,261-284)
+ *
+ * Conventions
+ *   - plain C: pointers, ints, doubles; no torch / C++ types.
+ *   - every `double*` is a DEVICE pointer unless its name ends in `_host`.
+ *   - a field is a dense fp64 array F[k][j][i] with extents ny_ext{nz,ny,nx} (i fastest):
+ *     the reference's `view('i')` (core/variables.py:146-148).  Extents are LOCAL array
+ *     extents, halo rows included on the sides that have a neighbour
+ *     (core/mpi/topology.py:253-304).  As in the Fortran, boundary closures are keyed to the
+ *     array ends.
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); calls are
+ *     asynchronous except where stated.  One ny_ctx per GPU, not thread-safe per context.
+ *   - return value: 0 on success, negative ny_status on failure; ny_last_error() gives text.
+ *     The library never calls exit() (the Fortran `stop`s, mg_setup.f90:337-340,377-381).
+ *   - arithmetic: fp64, no FMA contraction, operation order of the Fortran source, including
+ *     its REAL(4) literal/tau5 roundings (core/weno.f90:34-46) => bit-identical to the oracle.
+ */
+#ifndef NYLES_B200_H
+#define NYLES_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ny_ctx ny_ctx;
+typedef struct ny_mg ny_mg;
+
+typedef struct ny_ext { int nz, ny, nx; } ny_ext;
+
+typedef enum ny_status {
+    NY_OK = 0,
+    NY_ERR_ARG = -1,       /* bad argument (null pointer, extent < 5 on a WENO axis, ...) */
+    NY_ERR_CUDA = -2,      /* CUDA runtime error */
+    NY_ERR_GRID = -3,      /* grid cannot be coarsened by the multigrid hierarchy */
+    NY_ERR_COMM = -4       /* communicator error */
+} ny_status;
+
+/* mgfor topology enum, core/mgfor/mg_enums.f90:5-7 */
+enum { NY_TOPO_CLOSED = 1, NY_TOPO_XPERIO = 2, NY_TOPO_YPERIO = 3, NY_TOPO_ZPERIO = 4,
+       NY_TOPO_XYPERIO = 5, NY_TOPO_XYZPERIO = 6 };
+
+/* level-array selector of set/get_pyarray, core/mgfor/pytools.f90:17-62 */
+enum { NY_MG_X = 1, NY_MG_B = 2, NY_MG_R = 3, NY_MG_Y = 4, NY_MG_DIAG = 5, NY_MG_IDIAG = 6,
+       NY_MG_MSK = 7, NY_MG_RCOEF = 8, NY_MG_PCOEF = 9 };
+
+/* single multigrid operations (core/mgfor/operators.f90:127-244), exposed for parity tests */
+enum { NY_MG_OP_SMOOTH = 1, NY_MG_OP_RESIDUAL = 2, NY_MG_OP_RESTRICTION = 3,
+       NY_MG_OP_PROLONGATION = 4, NY_MG_OP_VCYCLE = 5 };
+
+typedef struct ny_mg_stats {          /* MG_Stats, core/mgfor/mg_types.f90:45-48 (+normb, history) */
+    int nite;                         /* V-cycles done by the last solve */
+    int nres;                         /* entries used in reshist */
+    double res;                       /* sum(msk r^2)/sum(msk b^2) when the loop exited */
+    double normb;                     /* sum(msk b^2) */
+    double reshist[32];               /* res before the 1st cycle, after cycle 1, ... */
+} ny_mg_stats;
+
+/* ---- context ---------------------------------------------------------------------- */
+int  ny_init(int device, ny_ctx** out);
+void ny_free(ny_ctx* ctx);
+const char* ny_last_error(void);
+int  ny_version(void);
+/* number of kernel launches issued through this context since creation / last reset */
+long long ny_launch_count(ny_ctx* ctx);
+void ny_launch_count_reset(ny_ctx* ctx);
+
+/* ---- f2py kernel replacements ------------------------------------------------------ */
+/* fortran_vorticity.vorticity x3 as driven by core/vorticity.py:7-34 (fparam = f*dx*dy, 0 = off) */
+int ny_vorticity(ny_ctx*, const double* ux, const double* uy, const double* uz,
+                 double* wx, double* wy, double* wz, ny_ext e, double fparam, void* stream);
+
+/* fortran_upwind.upwind x3 as driven by core/tracer.py:44-72: dtrac = -div(U trac) (WENO) */
+int ny_upwind(ny_ctx*, const double* trac, const double* Ux, const double* Uy, const double* Uz,
+              double* dtrac, ny_ext e, void* stream);
+
+/* same with tracer diffusion interleaved per direction as core/tracer.py:72-77 does when
+ * last=True (coefficients = diff_coef*ids2 per axis) */
+int ny_upwind_diff(ny_ctx*, const double* trac, const double* Ux, const double* Uy, const double* Uz,
+                   double* dtrac, double cx, double cy, double cz, ny_ext e, void* stream);
+
+/* fortran_vortex_force.vortex_force_direc/_flip x3 as driven by core/vortex_force.py:69-81:
+ * du += vortex force (six WENO line sweeps) */
+int ny_vortex_force(ny_ctx*, const double* Ux, const double* Uy, const double* Uz,
+                    const double* wx, const double* wy, const double* wz,
+                    double* dux, double* duy, double* duz, ny_ext e, void* stream);
+
+/* fortran_kinenergy.kin x3 as driven by core/kinenergy.py:7-24 */
+int ny_kin(ny_ctx*, const double* ux, const double* uy, const double* uz, double* ke,
+           double idx2, double idy2, double idz2, ny_ext e, void* stream);
+
+/* fortran_bernoulli.gradke/gradkeandb as driven by core/bernoulli.py:14-32 (euler!=0: no b term) */
+int ny_bernoulli(ny_ctx*, const double* ke, const double* b, double* dux, double* duy, double* duz,
+                 double dz, int euler, ny_ext e, void* stream);
+
+/* fortran_bernoulli.div x3 as driven by core/projection.py:16-29 */
+int ny_div(ny_ctx*, const double* Ux, const double* Uy, const double* Uz, double* div,
+           ny_ext e, void* stream);
+
+/* fortran_bernoulli.gradke(p,u_d) x3, core/projection.py:84-87: u -= delta p */
+int ny_gradp(ny_ctx*, const double* p, double* ux, double* uy, double* uz, ny_ext e, void* stream);
+
+/* core/cov_to_contra.py:4-20: U = u*idx2, V = v*idy2, W = w*idz2 */
+int ny_U_from_u(ny_ctx*, const double* ux, const double* uy, const double* uz,
+                double* Ux, double* Uy, double* Uz, double idx2, double idy2, double idz2,
+                ny_ext e, void* stream);
+
+/* fortran_dissipation.add_laplacian along all three axes (core/viscosity.py:3-9, tracer.py:74-77):
+ * dphi += sum_d coef_d * delta_d delta_d phi with zero-flux ends */
+int ny_add_laplacian(ny_ctx*, const double* phi, double* dphi, double cx, double cy, double cz,
+                     ny_ext e, void* stream);
+
+/* ---- fused forms of the same arithmetic (identical results, fewer passes over HBM) --- */
+/* whole right-hand side of model_les.LES.rhs / model_les_euler (core/model_les.py:130-144):
+ * db, du are OVERWRITTEN (the reference zeroes them first).  flags: bit0 euler (no tracer, no b),
+ * bit1 linear (no vortex force).  db may be null when euler. */
+int ny_rhs(ny_ctx*, const double* b, const double* Ux, const double* Uy, const double* Uz,
+           const double* wx, const double* wy, const double* wz, const double* ke,
+           double* db, double* dux, double* duy, double* duz,
+           double dz, int flags, ny_ext e, void* stream);
+
+/* ---- time schemes (core/timescheme.py:113-221), n = number of doubles ------------------ */
+int ny_ts_axpy(ny_ctx*, double* s, const double* ds, double a, long long n, void* stream);     /* s += a*ds */
+int ny_ts_lfam3_first(ny_ctx*, double* s, const double* ds, double* sb, double* sn, double dt,
+                      long long n, void* stream);
+int ny_ts_lfam3_pred(ny_ctx*, double* s, const double* ds, double* sb, double* sn, double dt,
+                     long long n, void* stream);
+int ny_ts_lfam3_corr(ny_ctx*, double* s, const double* ds, const double* sn, double dt,
+                     long long n, void* stream);
+int ny_ts_rk3_stage2(ny_ctx*, double* s, const double* ds0, const double* ds1, double dt,
+                     long long n, void* stream);
+int ny_ts_rk3_stage3(ny_ctx*, double* s, const double* ds0, const double* ds1, const double* ds2,
+                     double dt, long long n, void* stream);
+
+/* core/nyles.py:244-250: max over the whole arrays of U^2+V^2+W^2.  Synchronises `stream`
+ * and writes the scalar to *out_host. */
+int ny_max_speed2(ny_ctx*, const double* Ux, const double* Uy, const double* Uz, long long n,
+                  double* out_host, void* stream);
+
+/* ---- halo (core/mpi/halo.py:140-178 for one process: periodic wrap of nh-wide strips) ---
+ * per[3] = {z,y,x}: nonzero if that axis carries halos that wrap onto this same array. */
+int ny_halo_fill_self(ny_ctx*, double* f, ny_ext e, int nh, const int per[3], void* stream);
+
+/* ---- multigrid (libmgmod64.so replacement) --------------------------------------------- */
+/* get_ptrmg(npx=1,npy=1,nx,ny,nz,vertices=F,short=F,is3d=T,topology), mg_setup.f90:318-437 */
+int  ny_mg_create(ny_ctx*, int nx, int ny, int nz, int topology, ny_mg** out);
+void ny_mg_destroy(ny_mg*);
+int  ny_mg_nlevels(ny_mg*);
+/* get_pyshape: shape[0..2] = (nz+2nh, ny+2nh, nx+2nh) of level lev (1-based), numpy order */
+int  ny_mg_shape(ny_mg*, int lev, int shape[3]);
+/* MG_Param fields that matter (mg_types.f90:15-26); defaults maxite=20, tol=1e-6, omega=0.9 */
+int  ny_mg_set_param(ny_mg*, int maxite, double tol, double omega);
+/* set_pyarray / get_pyarray: whole level arrays, device to device */
+int  ny_mg_set_array(ny_mg*, int lev, int ivar, const double* src, void* stream);
+int  ny_mg_get_array(ny_mg*, int lev, int ivar, double* dst, void* stream);
+/* solvers.f90:8-33.  Synchronises `stream` once per V-cycle for the stopping test. */
+int  ny_mg_solve(ny_mg*, ny_mg_stats* stats_host, void* stream);
+/* mgfordriver.MG.solve_directly (core/mgfordriver.py:66-78) without the two host copies:
+ * b_mg[idx] = div; solve; p = x_mg[idx]*scale.  lo[3] = {k0,j0,i0}: offset of the model array
+ * inside the padded MG array (nh on sides without neighbour, 0 on sides with). */
+int  ny_mg_solve_directly(ny_mg*, double* p, const double* div, ny_ext e, const int lo[3],
+                          double scale, ny_mg_stats* stats_host, void* stream);
+int  ny_mg_op(ny_mg*, int op, int lev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NYLES_B200_H */

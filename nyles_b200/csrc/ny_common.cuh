@@ -1,0 +1,54 @@
+// Shared host/device helpers of libnyles_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdarg>
+#include <cstring>
+#include "../../include/nyles_b200.h"
+
+struct ny_ctx {
+    int device;
+    int num_sms;
+    long long launches;
+    double* d_scratch;        // reduction partials (device)
+    size_t scratch_doubles;
+    double* h_pinned;         // small pinned mailbox for scalars
+};
+
+void ny_set_error(const char* fmt, ...);
+
+#define NY_CUDA(call)                                                                    \
+    do {                                                                                 \
+        cudaError_t _e = (call);                                                         \
+        if (_e != cudaSuccess) {                                                         \
+            ny_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+            return NY_ERR_CUDA;                                                          \
+        }                                                                                \
+    } while (0)
+
+#define NY_CHECK_LAUNCH(ctx)                                                             \
+    do {                                                                                 \
+        (ctx)->launches++;                                                               \
+        cudaError_t _e = cudaPeekAtLastError();                                          \
+        if (_e != cudaSuccess) {                                                         \
+            ny_set_error("%s:%d kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+            return NY_ERR_CUDA;                                                          \
+        }                                                                                \
+    } while (0)
+
+#define NY_REQUIRE(cond, msg)                                                            \
+    do {                                                                                 \
+        if (!(cond)) { ny_set_error("%s: %s", __func__, msg); return NY_ERR_ARG; }       \
+    } while (0)
+
+static inline cudaStream_t ny_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// 3-D launch geometry for cell-parallel kernels: x covers i (coalesced), y covers j, z covers k.
+struct ny_grid3 { dim3 grid, block; };
+static inline ny_grid3 ny_cells_launch(int nz, int ny, int nx, int bx = 32, int by = 4, int bz = 2)
+{
+    ny_grid3 g;
+    g.block = dim3(bx, by, bz);
+    g.grid = dim3((nx + bx - 1) / bx, (ny + by - 1) / by, (nz + bz - 1) / bz);
+    return g;
+}

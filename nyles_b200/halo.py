@@ -1,0 +1,100 @@
+"""Halo filling, API of core/mpi/halo.py (``set_halo(param, state)`` -> ``.fill(Scalar|Vector|tensor)``).
+
+The reference exchanges 26 boxes per array with persistent MPI requests.  Here the domain is cut
+into slabs along z only (one GPU per slab), so a fill is:
+  1. the two z faces (nh contiguous planes each) exchanged with the slab neighbours through
+     torch.distributed (NCCL over NVLink; gloo in the CPU tests) -- or wrapped locally when the
+     z neighbour is this very rank (one slab, z-periodic);
+  2. the periodic x / y directions wrapped locally over ALL planes, halo planes included, which
+     reproduces the edge and corner boxes of the 26-neighbour exchange.
+"""
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from . import lib
+from . import mpitools
+
+
+class Halo(object):
+    def __init__(self, grid):
+        self.neighbours = grid["neighbours"]
+        self.nh = grid["nh"]
+        self.size = tuple(grid["size"])
+        self.domainindices = grid["domainindices"]
+        self.myrank = mpitools.get_myrank()
+        ng = self.neighbours
+        self.below = ng.get((-1, 0, 0))
+        self.above = ng.get((1, 0, 0))
+        self.yper = (0, -1, 0) in ng
+        self.xper = (0, 0, -1) in ng
+        for key, rank in ng.items():
+            if key[0] == 0 and rank != self.myrank:
+                raise NotImplementedError("nyles_b200 decomposes along z only (npx = npy = 1)")
+        self.z_self = self.below is not None and self.below == self.myrank and self.above == self.myrank
+        self.z_remote = (self.below is not None and self.below != self.myrank) or \
+                        (self.above is not None and self.above != self.myrank)
+
+    # ------------------------------------------------------------------ public
+    def fill(self, thing):
+        nature = type(thing).__name__
+        if nature == "Scalar":
+            self.fillarray(thing.tensor)
+        elif nature == "Vector":
+            self.fillvector(thing)
+        elif nature == "FieldView":
+            self.fillarray(thing.tensor)
+        elif isinstance(thing, torch.Tensor):
+            self.fillarray(thing)
+        else:
+            raise ValueError("try to fill halo with unidentified object")
+
+    def fillvector(self, vector):
+        self.fillarrays([vector[d].tensor for d in "ijk"])
+
+    def fillarray(self, x):
+        self.fillarrays([x])
+
+    def fillarrays(self, xs):
+        if self.z_remote:
+            self._exchange_z(xs)
+        per = (1 if self.z_self else 0, 1 if self.yper else 0, 1 if self.xper else 0)
+        if any(per):
+            for x in xs:
+                self._wrap(x, per)
+
+    # ------------------------------------------------------------------ pieces
+    def _wrap(self, x, per):
+        arr = (C.c_int * 3)(*per)
+        lib.check(lib.load().ny_halo_fill_self(lib.context(x.device), lib.ptr(x), lib.ext(x), self.nh,
+                                               C.byref(arr), lib.stream()))
+
+    def _exchange_z(self, xs):
+        nh = self.nh
+        ops = []
+        for x in xs:
+            if self.below is not None:
+                ops.append(dist.P2POp(dist.isend, x[nh:2 * nh], self.below))
+                ops.append(dist.P2POp(dist.irecv, x[0:nh], self.below))
+            if self.above is not None:
+                n = x.shape[0]
+                ops.append(dist.P2POp(dist.isend, x[n - 2 * nh:n - nh], self.above))
+                ops.append(dist.P2POp(dist.irecv, x[n - nh:n], self.above))
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
+
+def check_halo_width(procs, shape, nh):
+    """A sub-domain must be at least as wide as the halo it feeds (core/mpi/halo.py)."""
+    for p, s in zip(procs, shape):
+        if p > 1 and s < nh:
+            raise ValueError("subdomain narrower than the halo")
+
+
+def set_halo(param, state):
+    b = state.b
+    localgrid = {"shape": b.shape, "size": tuple(b.tensor.shape), "nh": param["nh"],
+                 "neighbours": param["neighbours"], "domainindices": b.domainindices, "extension": 6}
+    check_halo_width(param["procs"], b.shape, param["nh"])
+    return Halo(localgrid)

@@ -1,0 +1,146 @@
+"""LES model, API of core/model_les.py:31-175 (and, with euler=True, core/model_les_euler.py).
+
+At each step the model does not suppose that the previous velocity was divergence free; it
+projects after every update (Ferziger p.180), exactly like the reference:
+    rhs          : tracer advection, vortex force, Bernoulli term (+ viscosity, forcing)
+    diagnose_var : halo fills, U from u, pressure projection (multigrid), vorticity, kinetic energy
+All fields are CUDA tensors in one canonical layout; the operator modules call libnyles_b200.so.
+"""
+import pickle
+
+from . import variables as var
+from . import tracer
+from . import timescheme as ts
+from . import vortex_force as vortf
+from . import vorticity as vort
+from . import bernoulli as bern
+from . import kinenergy as kinetic
+from . import viscosity as visc
+from . import projection
+from . import cov_to_contra
+from . import halo
+from . import lib
+from .mgfordriver import MG
+from .timing import timing
+
+TOPOLOGY = {"closed": 1, "perio_xy": 5, "perio_xyz": 6}      # core/model_les.py:80-88
+
+
+class LES(object):
+    euler = False
+
+    def __init__(self, param, grid, linear=False, fused=True):
+        self.nonlinear = not linear
+        self.fused = fused                    # one fused RHS launch pair instead of the per-operator calls
+        self.grid = grid
+        self.traclist = [] if self.euler else ["b"]
+        modelvar = dict(var.modelvar)
+        if not self.euler:
+            for i in range(param["n_tracers"]):
+                nick = "t{}".format(i)
+                self.traclist.append(nick)
+                modelvar[nick] = var.ModelVariable("scalar", "tracer{}".format(i), "", True)
+        self.state = var.get_state(param, modelvar)
+        self.halo = halo.set_halo(param, self.state)
+        self.neighbours = param["neighbours"]
+        self.timescheme = ts.Timescheme(param, self.state)
+        self.timescheme.set(self.rhs, self.diagnose_var)
+        self.orderA, self.orderVF, self.orderKE = param["orderA"], param["orderVF"], param["orderKE"]
+        self.rotating = param["rotating"]
+        self.forced = param["forced"]
+        self.forcing = None
+        self.diff_coef = param["diff_coef"]
+        self.add_viscosity = "u" in self.diff_coef.keys()
+        if self.add_viscosity:
+            self.viscosity = self.diff_coef["u"]
+        self.tracer = tracer.Tracer_numerics(param, grid, self.traclist, self.orderA, self.diff_coef)
+        # Coriolis parameter as a covariant quantity: f * horizontal cell area (model_les.py:61-67)
+        self.fparameter = param["coriolis"] * self.grid.dx * self.grid.dy if self.rotating else 0.
+
+        geometry = param["geometry"]
+        if geometry not in TOPOLOGY or (self.euler and geometry == "perio_xy"):
+            raise ValueError("geometry %r is not supported by the multigrid (model_les.py:80-88)" % geometry)
+        if param["npz"] > 1:
+            from .mg_slab import SlabMG
+            self.mg = SlabMG(param, grid, TOPOLOGY[geometry])
+        else:
+            self.mg = MG(grid.npx, grid.npy, param["nx"], param["ny"], param["nz"], param["nh"], TOPOLOGY[geometry])
+        self.mg.preallocate_for_nyles(grid.dx, param["neighbours"], self.halo)
+        self.stats = []
+
+    # ------------------------------------------------------------------
+    @timing
+    def diagnose_var(self, state):
+        if not self.euler:                    # model_les_euler.py:98-99 has these two fills commented out
+            self.halo.fill(state.b)
+            self.halo.fill(state.u)
+        cov_to_contra.U_from_u(state, self.grid)
+        projection.compute_p(self.mg, state, self.grid, self.neighbours)
+        self.halo.fill(state.u)
+        cov_to_contra.U_from_u(state, self.grid)
+        if self.nonlinear:
+            vort.vorticity(state, self.fparameter)
+            kinetic.kinenergy(state, self.grid, self.orderKE)
+            self.halo.fill(state.vor)
+            self.halo.fill(state.ke)
+
+    @timing
+    def rhs(self, state, t, dstate, last=False):
+        extra_tracers = len(self.traclist) > 1
+        if self.fused:
+            self._rhs_fused(state, dstate)
+            if extra_tracers:
+                saved, self.tracer.traclist = self.tracer.traclist, self.traclist[1:]
+                self.tracer.rhstrac(state, dstate)
+                self.tracer.traclist = saved
+        else:
+            reset_state(dstate)
+            if not self.euler:
+                self.tracer.rhstrac(state, dstate)     # model_les.py:133: `last` is not forwarded
+            if self.nonlinear:
+                vortf.vortex_force(state, dstate, self.orderVF)
+            if self.euler:
+                bern.bernoulli_euler(state, dstate, self.grid)
+            else:
+                bern.bernoulli(state, dstate, self.grid)
+        if last and self.add_viscosity:
+            visc.add_viscosity(self.grid, state, dstate, self.viscosity)
+        if self.forced:
+            self.forcing.add(state, dstate, t)
+
+    def _rhs_fused(self, state, dstate):
+        U, w, du = state.U, state.vor, dstate.u
+        t = U["i"].tensor
+        flags = (1 if self.euler else 0) | (0 if self.nonlinear else 2)
+        lib.check(lib.load().ny_rhs(
+            lib.context(t.device), lib.ptr(None if self.euler else state.b.tensor),
+            lib.ptr(U["i"].tensor), lib.ptr(U["j"].tensor), lib.ptr(U["k"].tensor),
+            lib.ptr(w["i"].tensor), lib.ptr(w["j"].tensor), lib.ptr(w["k"].tensor), lib.ptr(state.ke.tensor),
+            lib.ptr(None if self.euler else dstate.b.tensor),
+            lib.ptr(du["i"].tensor), lib.ptr(du["j"].tensor), lib.ptr(du["k"].tensor),
+            self.grid.dz, flags, lib.ext(t), lib.stream()))
+        if self.euler:
+            dstate.b.tensor.zero_()
+
+    @timing
+    def forward(self, t, dt):
+        self.timescheme.forward(self.state, t, dt)
+        return self.mg.stats["blowup"]
+
+    def update_stats(self):
+        stats = dict(self.mg.stats)
+        stats["maxdiv"] = self.state.div.tensor.abs().max().item()
+        self.stats += [stats]
+
+    def write_stats(self, path):
+        with open("%s/stats.pkl" % path, "bw") as fid:
+            pickle.dump(self.stats, fid)
+
+
+def reset_state(state):
+    for var_name, var_type in state.toc.items():
+        if var_type == "scalar":
+            state.get(var_name).tensor.zero_()
+        else:
+            for i in "ijk":
+                state.get(var_name)[i].tensor.zero_()

@@ -1,0 +1,130 @@
+"""The Nyles main class, API of core/nyles.py:22-260: Nyles(user_param), .run(), .compute_dt().
+
+One process per GPU (torchrun); the process grid is [npz, 1, 1] -- slabs along z.
+"""
+import pickle
+import sys
+from time import time
+
+import numpy as np
+import torch
+
+from . import grid as grid_module
+from . import lib
+from . import model_les
+from . import model_les_euler
+from . import mpitools
+from . import nylesIO
+from . import timing
+from . import topology as topo
+
+
+class Nyles(object):
+    def __init__(self, user_param):
+        user_param.check()
+        user_param.freeze()
+        param = user_param.view_parameters()
+        self.param = param
+        npx, npy, npz = param["npx"], param["npy"], param["npz"]
+        if npx != 1 or npy != 1:
+            raise NotImplementedError("nyles_b200 decomposes along z only: set npx = npy = 1, npz = #GPUs")
+        param["nx"] = param["global_nx"] // npx
+        param["ny"] = param["global_ny"] // npy
+        param["nz"] = param["global_nz"] // npz
+
+        topo.topology = param["geometry"]
+        procs = [npz, npy, npx]
+        myrank = mpitools.get_myrank(procs)
+        loc = topo.rank2loc(myrank, procs)
+        param["procs"] = procs
+        param["myrank"] = myrank
+        param["neighbours"] = topo.get_neighbours(loc, procs)
+        param["loc"] = loc
+        self.myrank = myrank
+        if myrank == 0 and param.get("verbose", True):
+            print("-" * 80)
+            self.banner()
+
+        self.grid = grid_module.Grid(param)
+        self.IO = nylesIO.NylesIO(param)
+        if myrank == 0 and self.IO.enabled:
+            with open(self.IO.output_directory + "/param.pkl", "wb") as fid:
+                pickle.dump({k: v for k, v in param.items()}, fid)
+        self.initiate(param)
+
+    def initiate(self, param):
+        name = param["modelname"]
+        if name == "LES":
+            self.model = model_les.LES(param, self.grid)
+        elif name == "Euler3d":
+            self.model = model_les_euler.LES(param, self.grid)
+        elif name == "linear":
+            self.model = model_les.LES(param, self.grid, linear=True)
+        else:
+            raise NotImplementedError("modelname %r is outside the LES hot path of nyles_b200" % name)
+        self.tend = param["tend"]
+        self.auto_dt = param["auto_dt"]
+        self.dt0 = param["dt"]
+        self.cfl = param["cfl"]
+        self.dt_max = param["dt_max"]
+        self.plotting = None
+        self.gridcellpersubdom = param["nx"] * param["ny"] * param["nz"]
+
+    def run(self, max_steps=None, quiet=False):
+        t, n = 0.0, 0
+        self.model.diagnose_var(self.model.state)
+        self.IO.init(self.model.state, self.grid, t, n)
+        if self.myrank == 0 and self.IO.enabled:
+            self.IO.backup_scriptfile(sys.argv[0])
+        time_length = len(str(int(self.tend))) + 3
+        time_string = "\r" + ", ".join([
+            "n = {:3d}", "t = {:" + str(time_length) + ".2f}/{:" + str(time_length) + ".2f}",
+            "dt = {:.4f}", "perf = {:.2e}"])
+        stop = False
+        realtime0 = time()
+        while not stop:
+            dt = self.compute_dt()
+            blowup = self.model.forward(t, dt)
+            t += dt
+            n += 1
+            stop = self.IO.write(self.model.state, t, n)
+            if self.myrank == 0 and not quiet:
+                realtime = time()
+                # wall time per iteration per grid cell of the subdomain (nyles.py:174-182)
+                perf = (realtime - realtime0) / self.gridcellpersubdom
+                realtime0 = realtime
+                print(time_string.format(n, t, self.tend, dt, perf), end="")
+            localmood = 1. if (blowup or not np.isfinite(dt)) else 0.
+            if mpitools.global_sum(localmood) > 0.:
+                if self.myrank == 0:
+                    print("\nBLOW UP!")
+                self.IO.t_next_hist = t
+                self.IO.write(self.model.state, t, n)
+                stop = True
+            if t >= self.tend or stop or (max_steps is not None and n >= max_steps):
+                break
+        if self.myrank == 0 and not quiet:
+            print()
+            print("Job is aborted" if stop else "Job completed as expected")
+        self.IO.finalize(self.model.state, t, n)
+        if self.IO.enabled:
+            self.model.write_stats(self.IO.output_directory)
+            timing.write_timings(self.IO.output_directory)
+        self.t, self.n = t, n
+
+    def compute_dt(self):
+        """dt = min(cfl / max|U|, dt_max) from the contravariant velocity (nyles.py:227-260)."""
+        if not self.auto_dt:
+            return self.dt0
+        U = self.model.state.U
+        t = U["i"].tensor
+        out = lib.C.c_double()
+        lib.check(lib.load().ny_max_speed2(lib.context(t.device), lib.ptr(U["i"].tensor), lib.ptr(U["j"].tensor),
+                                           lib.ptr(U["k"].tensor), t.numel(), lib.C.byref(out), lib.stream()))
+        U_max = mpitools.global_max(float(np.sqrt(out.value)))
+        if U_max == 0.0:
+            return self.dt_max
+        return min(self.cfl / U_max, self.dt_max)
+
+    def banner(self):
+        print("nyles_b200: B200-native LES time step with the Nyles API")

@@ -1,0 +1,299 @@
+"""GPU parity, operator level: every entry point of libnyles_b200.so against the CPU oracle on the
+same seeded inputs.  The arithmetic is fp64 in the Fortran's operation order without FMA, so the
+bar is BIT-EXACT (np.array_equal; +0 == -0), far inside north_star's 1e-12."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import model as M
+from oracle.kernels import Kernels
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [(5, 5, 5), (6, 7, 9), (8, 8, 16), (13, 10, 37), (32, 24, 40)]     # (nz, ny, nx); ragged on purpose
+
+
+@pytest.fixture(scope="module")
+def K():
+    return Kernels("strict")
+
+
+@pytest.fixture(scope="module")
+def L():
+    from nyles_b200 import lib
+    return lib
+
+
+def dev(a):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64).cuda()
+
+
+def host(t):
+    return t.cpu().numpy()
+
+
+def views(a):
+    """(k,j,i) array -> the reference's three orientations as strided views."""
+    return {"i": a, "j": a.transpose(2, 0, 1), "k": a.transpose(1, 2, 0)}
+
+
+def flip(a, d):
+    return views(a)[{"i": "j", "j": "k", "k": "i"}[d]]
+
+
+def rand_fields(shape, n, seed, scale=1.0):
+    rng = np.random.default_rng(seed)
+    return [scale * rng.standard_normal(shape) for _ in range(n)]
+
+
+# --------------------------------------------------------------------------- oracle drivers
+def oracle_vorticity(K, u, fparam):
+    w = [np.full_like(u[0], 7.0) for _ in range(3)]       # sentinel: untouched rows must stay
+    perm = {"i": ("k", "j"), "j": ("i", "k"), "k": ("j", "i")}
+    comp = dict(zip("ijk", range(3)))
+    for dirk in "ijk":
+        dirj, diri = perm[dirk]
+        wk = flip(w[comp[dirk]], dirk)
+        K.vorticity(flip(u[comp[diri]], dirk), flip(u[comp[dirj]], dirk), wk)
+        if fparam > 0 and dirk == "k":
+            wk[:, :-1, :-1] += fparam
+    return w
+
+
+def oracle_vortex_force(K, U, w, du):
+    comp = dict(zip("ijk", range(3)))
+    for k, j, i in ["ikj", "jik", "kji"]:
+        K.vortex_force_direc(flip(U[comp[k]], j), flip(w[comp[j]], j), flip(du[comp[i]], j))
+        K.vortex_force_flip(flip(U[comp[i]], j), flip(w[comp[j]], j), flip(du[comp[k]], j))
+
+
+def oracle_upwind(K, trac, U, coefs=None):
+    d = np.full_like(trac, 3.0)
+    for n, ax in enumerate("ijk"):
+        dv = views(d)[ax]
+        if ax == "i":
+            dv[...] = 0.0
+        K.upwind(views(trac)[ax], views(U[n])[ax], dv)
+        if coefs is not None:
+            K.add_laplacian(views(trac)[ax], dv, coefs[n])
+    return d
+
+
+# --------------------------------------------------------------------------- tests
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("fparam", [0.0, 0.37])
+def test_vorticity(K, L, shape, fparam):
+    u = rand_fields(shape, 3, 1)
+    ref = oracle_vorticity(K, u, fparam)
+    du = [dev(a) for a in u]
+    w = [torch.full(shape, 7.0, dtype=torch.float64, device="cuda") for _ in range(3)]
+    L.check(L.load().ny_vorticity(L.context(), *[L.ptr(t) for t in du], *[L.ptr(t) for t in w],
+                                  L.ext(du[0]), fparam, L.stream()))
+    for a, b in zip(ref, w):
+        assert np.array_equal(a, host(b))
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_kin_div_gradp_scale(K, L, shape):
+    u = rand_fields(shape, 3, 2)
+    ids2 = (3.7, 0.9, 11.3)
+    # kinetic energy
+    ke = np.full(shape, 5.0)
+    for n, ax in enumerate("ijk"):
+        kv = views(ke)[ax]
+        if ax == "i":
+            kv[...] = 0.0
+        K.kin(views(u[n])[ax], views(u[n])[ax], kv, ids2[n])
+    du = [dev(a) for a in u]
+    gke = torch.empty(shape, dtype=torch.float64, device="cuda")
+    L.check(L.load().ny_kin(L.context(), *[L.ptr(t) for t in du], L.ptr(gke), *ids2, L.ext(gke), L.stream()))
+    assert np.array_equal(ke, host(gke))
+    # U = u * ids2
+    gU = [torch.empty_like(t) for t in du]
+    L.check(L.load().ny_U_from_u(L.context(), *[L.ptr(t) for t in du], *[L.ptr(t) for t in gU], *ids2,
+                                 L.ext(gke), L.stream()))
+    U = [u[n] * ids2[n] for n in range(3)]
+    for a, b in zip(U, gU):
+        assert np.array_equal(a, host(b))
+    # divergence
+    div = np.full(shape, 9.0)
+    for n, ax in enumerate("ijk"):
+        K.div(views(div)[ax], views(U[n])[ax], n)
+    gdiv = torch.empty(shape, dtype=torch.float64, device="cuda")
+    L.check(L.load().ny_div(L.context(), *[L.ptr(t) for t in gU], L.ptr(gdiv), L.ext(gdiv), L.stream()))
+    assert np.array_equal(div, host(gdiv))
+    # u -= grad p
+    p = rand_fields(shape, 1, 3)[0]
+    uu = [a.copy() for a in u]
+    for n, ax in enumerate("ijk"):
+        K.gradke(views(p)[ax], views(uu[n])[ax])
+    gp = dev(p)
+    L.check(L.load().ny_gradp(L.context(), L.ptr(gp), *[L.ptr(t) for t in du], L.ext(gp), L.stream()))
+    for a, b in zip(uu, du):
+        assert np.array_equal(a, host(b))
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("seed", [10, 11])
+def test_upwind(K, L, shape, seed):
+    trac, Ux, Uy, Uz = rand_fields(shape, 4, seed)
+    ref = oracle_upwind(K, trac, [Ux, Uy, Uz])
+    g = [dev(a) for a in (trac, Ux, Uy, Uz)]
+    out = torch.full(shape, 3.0, dtype=torch.float64, device="cuda")
+    L.check(L.load().ny_upwind(L.context(), *[L.ptr(t) for t in g], L.ptr(out), L.ext(out), L.stream()))
+    assert np.array_equal(ref, host(out))
+    # with interleaved diffusion (tracer.py:72-77, last=True)
+    coefs = (0.3, 0.11, 0.7)
+    ref = oracle_upwind(K, trac, [Ux, Uy, Uz], coefs)
+    L.check(L.load().ny_upwind_diff(L.context(), *[L.ptr(t) for t in g], L.ptr(out), *coefs, L.ext(out), L.stream()))
+    assert np.array_equal(ref, host(out))
+
+
+def test_upwind_smooth_and_zero_velocity(K, L):
+    """sign test is strictly u > 0 (weno.f90:114): zero and negative-zero velocities take the else branch."""
+    shape = (8, 9, 12)
+    z, y, x = np.meshgrid(*[np.linspace(0, 1, n) for n in shape], indexing="ij")
+    trac = np.sin(2 * np.pi * x) * np.cos(2 * np.pi * y) + z
+    U = [np.zeros(shape), -np.zeros(shape), np.where(x > 0.5, 1.0, -1.0) * 0.3]
+    ref = oracle_upwind(K, trac, U)
+    g = [dev(a) for a in [trac] + U]
+    out = torch.empty(shape, dtype=torch.float64, device="cuda")
+    L.check(L.load().ny_upwind(L.context(), *[L.ptr(t) for t in g], L.ptr(out), L.ext(out), L.stream()))
+    assert np.array_equal(ref, host(out))
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_vortex_force_and_bernoulli(K, L, shape):
+    U = rand_fields(shape, 3, 20)
+    w = rand_fields(shape, 3, 21)
+    du0 = rand_fields(shape, 3, 22)
+    ke, b = rand_fields(shape, 2, 23)
+    dz = 0.125
+    ref = [a.copy() for a in du0]
+    oracle_vortex_force(K, U, w, ref)
+    gU, gw, gdu = [dev(a) for a in U], [dev(a) for a in w], [dev(a) for a in du0]
+    L.check(L.load().ny_vortex_force(L.context(), *[L.ptr(t) for t in gU + gw + gdu], L.ext(gU[0]), L.stream()))
+    for a, t in zip(ref, gdu):
+        assert np.array_equal(a, host(t))
+    # bernoulli on top (LES and Euler flavours)
+    for euler in (0, 1):
+        r2 = [a.copy() for a in ref]
+        for n, ax in enumerate("ijk"):
+            if ax == "k" and not euler:
+                K.gradkeandb(views(ke)[ax], views(b)[ax], views(r2[n])[ax], dz)
+            else:
+                K.gradke(views(ke)[ax], views(r2[n])[ax])
+        g2 = [dev(a) for a in ref]
+        L.check(L.load().ny_bernoulli(L.context(), L.ptr(dev(ke)), L.ptr(dev(b)), *[L.ptr(t) for t in g2],
+                                      dz, euler, L.ext(g2[0]), L.stream()))
+        for a, t in zip(r2, g2):
+            assert np.array_equal(a, host(t))
+
+
+@pytest.mark.parametrize("shape", SHAPES[1:])
+@pytest.mark.parametrize("flags", [0, 1, 2])
+def test_fused_rhs_equals_operator_sequence(K, L, shape, flags):
+    euler, linear = flags & 1, flags & 2
+    b, ke = rand_fields(shape, 2, 30)
+    U = rand_fields(shape, 3, 31)
+    w = rand_fields(shape, 3, 32)
+    dz = 0.25
+    db = oracle_upwind(K, b, U)
+    du = [np.zeros(shape) for _ in range(3)]
+    if not linear:
+        oracle_vortex_force(K, U, w, du)
+    for n, ax in enumerate("ijk"):
+        if ax == "k" and not euler:
+            K.gradkeandb(views(ke)[ax], views(b)[ax], views(du[n])[ax], dz)
+        else:
+            K.gradke(views(ke)[ax], views(du[n])[ax])
+    gb, gke, gU, gw = dev(b), dev(ke), [dev(a) for a in U], [dev(a) for a in w]
+    gdb = torch.full(shape, 4.0, dtype=torch.float64, device="cuda")
+    gdu = [torch.full(shape, 4.0, dtype=torch.float64, device="cuda") for _ in range(3)]
+    L.check(L.load().ny_rhs(L.context(), L.ptr(gb), *[L.ptr(t) for t in gU + gw], L.ptr(gke), L.ptr(gdb),
+                            *[L.ptr(t) for t in gdu], dz, flags, L.ext(gb), L.stream()))
+    if not euler:
+        assert np.array_equal(db, host(gdb))
+    for a, t in zip(du, gdu):
+        assert np.array_equal(a, host(t))
+
+
+@pytest.mark.parametrize("shape", SHAPES[:3])
+def test_add_laplacian(K, L, shape):
+    phi, dphi = rand_fields(shape, 2, 40)
+    coefs = (0.2, 0.5, 0.9)
+    ref = dphi.copy()
+    for n, ax in enumerate("ijk"):
+        K.add_laplacian(views(phi)[ax], views(ref)[ax], coefs[n])
+    g = dev(dphi)
+    L.check(L.load().ny_add_laplacian(L.context(), L.ptr(dev(phi)), L.ptr(g), *coefs, L.ext(g), L.stream()))
+    assert np.array_equal(ref, host(g))
+
+
+def test_extent_guard(L):
+    """flux1d reads out of bounds below 5 cells (weno.f90:106-153): the library refuses instead."""
+    t = torch.zeros((4, 8, 8), dtype=torch.float64, device="cuda")
+    rc = L.load().ny_upwind(L.context(), L.ptr(t), L.ptr(t), L.ptr(t), L.ptr(t), L.ptr(t), L.ext(t), L.stream())
+    assert rc == -1 and b"extent" in L.load().ny_last_error()
+
+
+def test_timescheme_kernels(L):
+    n = 100003
+    rng = np.random.default_rng(50)
+    s, ds, sb, d1, d2 = [rng.standard_normal(n) for _ in range(5)]
+    dt = 0.0371
+    ctx, lib = L.context(), L.load()
+
+    def run(fn, arrays, *scalars):
+        g = [dev(a) for a in arrays]
+        L.check(fn(ctx, *[L.ptr(t) for t in g], *scalars, n, L.stream()))
+        return [host(t) for t in g]
+
+    out = run(lib.ny_ts_axpy, [s, ds], dt)
+    r = s.copy(); r += dt * ds
+    assert np.array_equal(out[0], r)
+    out = run(lib.ny_ts_lfam3_first, [s, ds, sb, d1], dt)
+    r = s.copy(); r += dt * ds
+    assert np.array_equal(out[0], r) and np.array_equal(out[2], s) and np.array_equal(out[3], s)
+    out = run(lib.ny_ts_lfam3_pred, [s, ds, sb, d1], dt)
+    r = sb + (2. * dt) * ds
+    r = (1. / 12.) * (5. * r + 8. * s - sb)
+    assert np.array_equal(out[0], r) and np.array_equal(out[2], s) and np.array_equal(out[3], s)
+    out = run(lib.ny_ts_lfam3_corr, [s, ds, sb], dt)
+    assert np.array_equal(out[0], sb + dt * ds)
+    out = run(lib.ny_ts_rk3_stage2, [s, ds, d1], dt)
+    r = s.copy(); r += (dt / 4.) * (d1 - 3 * ds)
+    assert np.array_equal(out[0], r)
+    out = run(lib.ny_ts_rk3_stage3, [s, ds, d1, d2], dt)
+    r = s.copy(); r += (dt / 12.) * (8 * d2 - ds - d1)
+    assert np.array_equal(out[0], r)
+
+
+def test_max_speed2(L):
+    n = 300007
+    rng = np.random.default_rng(60)
+    U, V, W = [rng.standard_normal(n) for _ in range(3)]
+    out = C.c_double()
+    L.check(L.load().ny_max_speed2(L.context(), L.ptr(dev(U)), L.ptr(dev(V)), L.ptr(dev(W)), n, C.byref(out), L.stream()))
+    assert out.value == np.max(U ** 2 + V ** 2 + W ** 2)
+    U[1234] = np.nan
+    L.check(L.load().ny_max_speed2(L.context(), L.ptr(dev(U)), L.ptr(dev(V)), L.ptr(dev(W)), n, C.byref(out), L.stream()))
+    assert np.isnan(out.value)
+
+
+@pytest.mark.parametrize("geometry", ["closed", "perio_x", "perio_y", "perio_xy", "perio_xyz"])
+def test_halo_fill_self(L, geometry):
+    from nyles_b200 import halo as H, variables as V
+    p = M.make_param(9, 7, 8, geometry=geometry)
+    p["device"] = "cuda"
+    s = V.Scalar(p, "b", "b", "")
+    oracle_s = M.Scalar(p, "b")
+    rng = np.random.default_rng(70)
+    oracle_s.data[...] = rng.standard_normal(oracle_s.data.shape)
+    s.tensor.copy_(dev(oracle_s.data))
+    M.Halo(p, oracle_s).fill(oracle_s)
+    st = type("S", (), {"b": s})
+    H.set_halo(p, st).fill(s)
+    assert np.array_equal(oracle_s.data, host(s.tensor))

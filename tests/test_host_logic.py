@@ -1,0 +1,148 @@
+"""CPU tests: C-ABI surface, parameters, topology, storage/views and grid of the host layer."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "nyles_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ny_[A-Za-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    """The shared library loads without a GPU and exports exactly what include/nyles_b200.h declares."""
+    from nyles_b200 import lib
+    names = header_symbols()
+    assert len(names) >= 30
+    L = lib.load()
+    for n in names:
+        assert isinstance(getattr(L, n), ctypes._CFuncPtr), n
+    assert sorted(lib.EXPORTED) == names, "lib.py prototypes and the header disagree"
+    assert L.ny_version() >= 100
+
+
+def test_no_device_means_loud_failure():
+    import torch
+    from nyles_b200 import lib
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible")
+    with pytest.raises(lib.NylesB200Error):
+        lib.context()
+    h = ctypes.c_void_p()
+    assert lib.load().ny_init(0, ctypes.byref(h)) < 0 and lib.load().ny_last_error()
+
+
+def test_parameters_defaults_and_validation():
+    """The thirteen failure modes exercised by core/parameters.py:344-427, on the rewritten class."""
+    from nyles_b200.parameters import UserParameters, UserParameterError, InextensibleDict
+    InextensibleDict.unfreeze()
+    p = UserParameters()
+    p.check()
+    v = p.view_parameters()
+    assert v["modelname"] == "LES" and v["geometry"] == "closed" and v["nh"] == 3
+    assert v["timestepping"] == "LFAM3" and v["global_nx"] == 64 and v["cfl"] == 1.0 and v["orderVF"] == 5
+    assert p.help("cfl") and p.possible_values("geometry")[0] == "closed"
+    with pytest.raises(ValueError):
+        p.help("nonsense")
+    with pytest.raises(UserParameterError):
+        p.model["newkey"] = 1
+
+    def bad(cat, key, value):
+        InextensibleDict.unfreeze()
+        q = UserParameters()
+        getattr(q, cat)[key] = value
+        with pytest.raises(UserParameterError):
+            q.check()
+
+    bad("model", "geometry", "open")
+    bad("model", "Lx", 0.0)
+    bad("model", "Lx", "1")
+    bad("model", "n_tracers", -1)
+    bad("time", "timestepping", "RK4")
+    bad("time", "dt", -0.1)
+    bad("discretization", "global_nx", 100)
+    bad("discretization", "orderA", 7)
+    bad("MPI", "npx", 3)
+    bad("MPI", "npz", 128)          # more sub-domains than grid points
+    bad("IO", "expname", "a/b")
+    bad("IO", "variables_in_history", "everything")
+    bad("animation", "iterations_per_frame", 0)
+    InextensibleDict.unfreeze()
+    q = UserParameters()
+    q.discretization["global_nx"] = 96        # 3 * 2^n is accepted by the parameter check
+    q.check()
+    q.freeze()
+    with pytest.raises(UserParameterError):
+        q.time["cfl"] = 0.5
+    InextensibleDict.unfreeze()
+
+
+def test_topology_neighbours_and_extents():
+    from nyles_b200 import topology as topo
+    procs = [2, 1, 1]
+    topo.topology = "closed"
+    n0 = topo.get_neighbours([0, 0, 0], procs)
+    n1 = topo.get_neighbours([1, 0, 0], procs)
+    assert n0 == {(1, 0, 0): 1} and n1 == {(-1, 0, 0): 0}
+    size, dom = topo.get_variable_shape([8, 8, 8], n0, 3)
+    assert size == [11, 8, 8] and dom == (0, 8, 0, 8, 0, 8)
+    size, dom = topo.get_variable_shape([8, 8, 8], n1, 3)
+    assert size == [11, 8, 8] and dom == (3, 11, 0, 8, 0, 8)
+    topo.topology = "perio_xyz"
+    n = topo.get_neighbours(0, [1, 1, 1])
+    assert len(n) == 26 and set(n.values()) == {0}
+    # symmetric connectivity (core/mpi/topology.py:224-250) on a 4-slab periodic column
+    procs = [4, 1, 1]
+    for r in range(4):
+        for d, other in topo.get_neighbours(r, procs).items():
+            back = topo.get_neighbours(other, procs)
+            assert back[tuple(-c for c in d)] == r
+    assert topo.rank2loc(3, [4, 1, 1]) == [3, 0, 0] and topo.loc2rank([3, 0, 0], [4, 1, 1]) == 3
+
+
+def test_scalar_views_alias_one_buffer():
+    from nyles_b200 import variables as V, topology as topo
+    topo.topology = "perio_xy"
+    p = dict(nx=4, ny=5, nz=6, nh=3, neighbours=topo.get_neighbours(0, [1, 1, 1]), device="cpu")
+    s = V.Scalar(p, "buoyancy", "b", "")
+    assert tuple(s.tensor.shape) == (6, 11, 10) and s.domainindices == (0, 6, 3, 8, 3, 7)
+    assert s.view("i").shape == (6, 11, 10) and s.view("j").shape == (10, 6, 11) and s.view("k").shape == (11, 10, 6)
+    assert s.flipview("i").shape == s.view("j").shape and s.flipview("k").shape == s.view("i").shape
+    vi = s.view("i")
+    vi[:] = np.arange(6 * 11 * 10, dtype=float).reshape(6, 11, 10)
+    # same element through the three index orders, no copy involved
+    assert s.view("j")[7, 2, 4] == s.view("i")[2, 4, 7] == s.view("k")[4, 7, 2]
+    vk = s.view("k")
+    vk[4, 7, 2] = -1.0
+    assert s.tensor[2, 4, 7].item() == -1.0
+    vi *= 2.0
+    assert s.tensor[2, 4, 7].item() == -2.0
+    assert isinstance(np.asarray(vi), np.ndarray) and (vi + 1.0).shape == (6, 11, 10)
+    st = V.get_state(p)
+    assert st.get_prognostic_scalars() == ["b", "u_i", "u_j", "u_k"]
+    assert st.get("u_j") is st.u["j"]
+    ds = st.duplicate_prognostic_variables()
+    assert sorted(ds.toc) == ["b", "u"]
+    with pytest.raises(ValueError):
+        s.view("x")
+
+
+def test_grid_matches_reference_formulas():
+    from nyles_b200 import grid as G, topology as topo
+    topo.topology = "perio_xyz"
+    p = dict(nx=8, ny=4, nz=4, npx=1, npy=1, npz=1, Lx=2.0, Ly=1.0, Lz=1.0, nh=3,
+             neighbours=topo.get_neighbours(0, [1, 1, 1]), loc=[0, 0, 0])
+    g = G.Grid(p)
+    assert g.dx == 0.25 and g.idx2 == 16.0 and g.ids2["k"] == 16.0
+    x = g.x_b.view("i")
+    assert x.shape == (10, 10, 14)
+    assert np.allclose(x[0, 0, :], (np.arange(14) + 0.5 - 3) * 0.25)
+    assert np.allclose(g.x_vel["i"].view("i")[0, 0, :], x[0, 0, :] + 0.125)
+    assert np.allclose(g.z_vor["i"].view("i")[:, 0, 0], (np.arange(10) + 0.5 - 3) * 0.25 + 0.125)
+    assert g.y_b.view("j").shape == (14, 10, 10)
