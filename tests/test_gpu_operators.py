@@ -186,7 +186,8 @@ def test_vortex_force_and_bernoulli(K, L, shape):
             else:
                 K.gradke(views(ke)[ax], views(r2[n])[ax])
         g2 = [dev(a) for a in ref]
-        L.check(L.load().ny_bernoulli(L.context(), L.ptr(dev(ke)), L.ptr(dev(b)), *[L.ptr(t) for t in g2],
+        gke, gb = dev(ke), dev(b)           # keep alive: a freed temporary's block is reused at once
+        L.check(L.load().ny_bernoulli(L.context(), L.ptr(gke), L.ptr(gb), *[L.ptr(t) for t in g2],
                                       dz, euler, L.ext(g2[0]), L.stream()))
         for a, t in zip(r2, g2):
             assert np.array_equal(a, host(t))
@@ -228,7 +229,8 @@ def test_add_laplacian(K, L, shape):
     for n, ax in enumerate("ijk"):
         K.add_laplacian(views(phi)[ax], views(ref)[ax], coefs[n])
     g = dev(dphi)
-    L.check(L.load().ny_add_laplacian(L.context(), L.ptr(dev(phi)), L.ptr(g), *coefs, L.ext(g), L.stream()))
+    gphi = dev(phi)
+    L.check(L.load().ny_add_laplacian(L.context(), L.ptr(gphi), L.ptr(g), *coefs, L.ext(g), L.stream()))
     assert np.array_equal(ref, host(g))
 
 
@@ -276,10 +278,12 @@ def test_max_speed2(L):
     rng = np.random.default_rng(60)
     U, V, W = [rng.standard_normal(n) for _ in range(3)]
     out = C.c_double()
-    L.check(L.load().ny_max_speed2(L.context(), L.ptr(dev(U)), L.ptr(dev(V)), L.ptr(dev(W)), n, C.byref(out), L.stream()))
+    g = [dev(U), dev(V), dev(W)]
+    L.check(L.load().ny_max_speed2(L.context(), *[L.ptr(t) for t in g], n, C.byref(out), L.stream()))
     assert out.value == np.max(U ** 2 + V ** 2 + W ** 2)
     U[1234] = np.nan
-    L.check(L.load().ny_max_speed2(L.context(), L.ptr(dev(U)), L.ptr(dev(V)), L.ptr(dev(W)), n, C.byref(out), L.stream()))
+    g = [dev(U), dev(V), dev(W)]
+    L.check(L.load().ny_max_speed2(L.context(), *[L.ptr(t) for t in g], n, C.byref(out), L.stream()))
     assert np.isnan(out.value)
 
 
