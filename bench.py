@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""Benchmark of the Nyles LES time step (RHS + multigrid projection) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+Metric (BASELINE.json): LES cell-updates/s, fp64, one "step" = one steady-state LFAM3 step
+(2 right-hand sides + 2 pressure projections) of the whole domain.  N > 1 is launched by
+torchrun, one rank per GPU; the domain is cut into z slabs (weak scaling: 512^3 cells per GPU).
+
+The JSON line follows the driver contract; extra keys:
+  roofline      dominant kernel family: algorithmic bytes per launch group / event-timed duration
+  roofline_step whole step against the operator-level byte model of SURVEY.md 8(d)
+  cpu_baseline  the CPU restatement of the reference (oracle/, OpenMP build) on the host cores
+  e2e           the same metric through Nyles.step_host(): state in pinned HOST buffers, uploaded
+                and downloaded inside every timed step
+`--impl reference` times the CPU restatement alone (the reference's Fortran cannot be built in
+this image: no gfortran / MPI).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "LES cell-updates/s (fp64, RHS+projection)"
+UNIT = "cell-updates/s"
+
+# ---- workloads ---------------------------------------------------------------
+WEAK_SHAPES = {1: (512, 512, 512), 2: (512, 512, 1024), 4: (512, 1024, 1024), 8: (1024, 1024, 1024)}  # (nx,ny,nz)
+
+
+def workload(name, n_gpus):
+    if name == "weak512":          # configs[4] (= configs[2] at N=1): RT instability, closed box, LES
+        nx, ny, nz = WEAK_SHAPES[n_gpus]
+        return dict(name="rayleigh-taylor 512^3 per GPU (weak-scaling sweep), closed, LES, LFAM3",
+                    nx=nx, ny=ny, nz=nz, dx=0.25, geometry="closed", modelname="LES", ic="rt",
+                    cfl=0.8, dt_max=0.1)
+    if name == "tgv256":           # configs[1]
+        return dict(name="taylor-green vortex 256^3, perio_xyz, Euler3d, LFAM3", nx=256, ny=256, nz=256 * n_gpus,
+                    dx=2 * np.pi / 256, geometry="perio_xyz", modelname="Euler3d", ic="tgv", cfl=0.8, dt_max=0.05)
+    if name == "lock":             # configs[0]
+        return dict(name="lock-exchange 128x32x32, closed, LES, LFAM3", nx=128, ny=32, nz=32 * n_gpus, dx=0.25,
+                    geometry="closed", modelname="LES", ic="lock", cfl=0.8, dt_max=0.1)
+    if name.startswith("rt"):      # rtN: cubic RT box of N^3 per GPU (used for the CPU sample)
+        n = int(name[2:])
+        return dict(name="rayleigh-taylor %d^3, closed, LES, LFAM3" % n, nx=n, ny=n, nz=n * n_gpus, dx=0.25,
+                    geometry="closed", modelname="LES", ic="rt", cfl=0.8, dt_max=0.1)
+    raise SystemExit("unknown workload %r" % name)
+
+
+def initial_condition(w, x, y, z, rank):
+    """b, u, v (canonical (k,j,i) arrays or None) from 1-D cell-centre coordinates of this rank."""
+    shape = (len(z), len(y), len(x))
+    Lz = w["nz"] * w["dx"]
+    dx = w["dx"]
+    rng = np.random.default_rng(1234 + rank)
+    if w["ic"] == "rt":            # experiments/rayleightaylor/RT.py:69-71
+        noise = 0.01 * rng.standard_normal(shape)
+        noise += (0.5 * Lz - z)[:, None, None]
+        noise /= dx
+        return np.tanh(noise, out=noise), None, None
+    if w["ic"] == "lock":          # experiments/lockechange/lockexchange.py:65-72
+        Lx = w["nx"] * dx
+        noise = 0.1 * rng.standard_normal(shape)
+        return np.tanh((x[None, None, :] + noise - 0.25 * Lx) / (2 * dx)), None, None
+    if w["ic"] == "tgv":           # experiments/taylorgreen/tgv.py:68-84 (covariant: times dx)
+        X, Y, Z = x[None, None, :], y[None, :, None], z[:, None, None]     # cell centres, as tgv.py does
+        u = np.sin(X + 1.2) * np.cos(Y + 1.8) * np.cos(Z + 0.5) * dx
+        v = -np.cos(X + 1.2) * np.sin(Y + 1.8) * np.cos(Z + 0.5) * dx
+        return None, u, v
+    raise ValueError(w["ic"])
+
+
+def bytes_per_cell_step(w, n_vc):
+    """Operator-level compulsory HBM bytes per cell per LFAM3 step."""
+    return (984.0 if w["modelname"] == "Euler3d" else 1080.0) + 199.0 * n_vc
+
+
+# ---- clocks --------------------------------------------------------------------------------
+class ClockSampler(object):
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---- CPU restatement of the reference (oracle) ------------------------------------------------
+def cpu_reference_run(w, steps, warmup):
+    """Time `steps` LFAM3 steps of the OpenMP build of the oracle on this host.  Returns
+    (cell-updates/s, ms per step, threads, v-cycles per step)."""
+    from oracle import model as M
+    threads = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
+    p = M.make_param(nx=w["nx"], ny=w["ny"], nz=w["nz"], geometry=w["geometry"], Lx=w["nx"] * w["dx"],
+                     Ly=w["ny"] * w["dx"], Lz=w["nz"] * w["dx"], modelname=w["modelname"], cfl=w["cfl"],
+                     dt_max=w["dt_max"])
+    o = M.LES(p, flavour="fast")
+    g = o.grid
+    b, u, v = initial_condition(w, g.x_b_1D, g.y_b_1D, g.z_b_1D, 0)
+    if b is not None:
+        o.state.b.view("i")[:] = b
+    if u is not None:
+        o.state.u["i"].view("i")[:] = u
+        o.state.u["j"].view("i")[:] = v
+    o.diagnose_var(o.state)
+    t = 0.0
+    for _ in range(1 + warmup):                    # Euler start-up step + warm-up
+        dt = o.compute_dt(); o.forward(t, dt); t += dt
+    nlog = len(o.mg_log)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        dt = o.compute_dt(); o.forward(t, dt); t += dt
+    wall = time.perf_counter() - t0
+    n_vc = sum(m[0] for m in o.mg_log[nlog:]) / float(steps)
+    cells = w["nx"] * w["ny"] * w["nz"]
+    return cells * steps / wall, 1e3 * wall / steps, threads, n_vc
+
+
+def cpu_model_string():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = workload(args.cpu_sample, 1)
+    w = workload(args.workload, args.gpus)
+    value, ms, threads, n_vc = cpu_reference_run(sample, args.steps, args.warmup)
+    desc = ("%s: same IC/geometry/model as the workload on a %dx%dx%d sub-box, %d LFAM3 steps after 1 Euler + %d "
+            "warm-up steps; rate is per cell" % (sample["name"], sample["nx"], sample["ny"], sample["nz"],
+                                                 args.steps, args.warmup))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": w["name"], "sample": desc, "vcycles_per_step": n_vc,
+                       "cpu": cpu_model_string()},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---- the B200 arm ---------------------------------------------------------------------------
+# algorithmic bytes per cell of one timed launch group of each kernel family ("Kernels")
+def family_bytes_per_cell(euler):
+    return {
+        "rhs_tracer": 40.0,                       # b, U x3 -> db
+        "rhs_momentum": 80.0 if euler else 88.0,  # U x3, vor x3, ke (, b) -> du x3
+        "vorticity_ke": 40.0,                     # vorticity: u x3 -> vor x3 (48); ke: u x3 -> ke (32); mean per group
+        "div": 32.0, "gradp": 56.0, "U_from_u": 48.0,
+        "timescheme": 36.0,                       # predictor 48, corrector 24 per field; mean per group
+        "maxspeed": 24.0,
+        "mg_smooth_fine": 24.0,                   # x, b -> x (two Jacobi sweeps fused in one pass)
+        "mg_residual_fine": 24.0,                 # x, b -> r
+        "mg_restrict_fine": 9.0, "mg_prolong_fine": 17.0, "mg_norm": 8.0,
+        "mg_down_fine": 25.0,                     # smooth + residual + restriction fused: x, b -> x, b_coarse
+        "mg_up_fine": 25.0,                       # prolongation + smooth (+ residual norm) fused: x, b, x_coarse -> x
+        "mg_embed_extract": 16.0,
+    }
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from nyles_b200 import lib, nyles, parameters
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit("bench.py --gpus %d must run under torchrun with %d ranks (found WORLD_SIZE=%d)"
+                         % (args.gpus, args.gpus, world))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: no CUDA device is visible (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    w = workload(args.workload, args.gpus)
+    parameters.InextensibleDict.unfreeze()
+    up = parameters.UserParameters()
+    up.model["modelname"] = w["modelname"]
+    up.model["geometry"] = w["geometry"]
+    up.model["Lx"], up.model["Ly"], up.model["Lz"] = w["nx"] * w["dx"], w["ny"] * w["dx"], w["nz"] * w["dx"]
+    up.discretization["global_nx"], up.discretization["global_ny"], up.discretization["global_nz"] = \
+        w["nx"], w["ny"], w["nz"]
+    up.MPI["npz"] = args.gpus
+    up.time["cfl"], up.time["dt_max"] = w["cfl"], w["dt_max"]
+    up.IO["datadir"] = ""                                   # no history output inside the benchmark
+    ny = nyles.Nyles(up)
+    model, g = ny.model, ny.grid
+    b, u, v = initial_condition(w, g.x_b_1D, g.y_b_1D, g.z_b_1D, rank)
+    if b is not None:
+        model.state.b.view("i")[:] = b
+    if u is not None:
+        model.state.u["i"].view("i")[:] = u
+        model.state.u["j"].view("i")[:] = v
+    del b, u, v
+    model.diagnose_var(model.state)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(t):
+        dt = ny.compute_dt()
+        model.forward(t, dt)
+        return t + dt
+
+    t = 0.0
+    t = step(t)                                            # Euler start-up step of LFAM3 (not steady state)
+    for _ in range(args.warmup):
+        t = step(t)
+
+    # ---- timed region 1: state resident in HBM ----------------------------------------------
+    cells = w["nx"] * w["ny"] * w["nz"]
+    euler = w["modelname"] == "Euler3d"
+    barrier()
+    lib.launch_count_reset()
+    lib.prof_start()
+    vc0 = model.mg.nvcycles
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        t = step(t)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = lib.launch_count()
+    prof = lib.prof_collect()
+    lib.prof_start(0)
+    n_vc = (model.mg.nvcycles - vc0) / float(args.steps)
+    if world > 1:
+        tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = tt.item()
+    value = cells * args.steps / (ms * 1e-3)
+
+    # ---- timed region 2: through the host-buffer API (e2e) -----------------------------------
+    host = ny.allocate_host_state()
+    for h, d in zip(host, ny.prognostic_tensors()):
+        h.copy_(d)
+    barrier()
+    e2_steps = max(1, min(args.steps, args.e2e_steps))
+    t = ny.step_host(t, host) + t                          # warm the pinned path once
+    barrier()
+    e0.record()
+    for _ in range(e2_steps):
+        t += ny.step_host(t, host)
+    e1.record()
+    barrier()
+    ms2 = e0.elapsed_time(e1)
+    if world > 1:
+        tt = torch.tensor([ms2], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms2 = tt.item()
+    state_bytes = sum(h.numel() * 8 for h in host) * world
+    e2e = {"value": cells * e2_steps / (ms2 * 1e-3), "unit": UNIT, "h2d_bytes_per_step": state_bytes,
+           "d2h_bytes_per_step": state_bytes + 8, "steps": e2_steps,
+           "api": "nyles_b200.nyles.Nyles.step_host (prognostic state in pinned host memory)"}
+    del host
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel family ------------------------------------------------
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except (OSError, ValueError):
+        pass
+    peak_gbs, peak_src = (peaks["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured copy)") if "hbm_gbs" in peaks \
+        else (6650.0, "fallback of B200_PROFILING.md")
+    fam = family_bytes_per_cell(euler)
+    local_cells = cells / world
+    timed = {k: v for k, v in prof.items() if v[1] > 0}
+    total_ms = sum(v[0] for v in timed.values())
+    top = max((k for k in timed if k in fam), key=lambda k: timed[k][0], default=None)
+    shares = {k: round(v[0] / (ms), 4) for k, v in sorted(timed.items(), key=lambda kv: -kv[1][0])}
+    if top is not None:
+        t_ms, n = timed[top]
+        achieved = fam[top] * local_cells / (t_ms / n * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+                    "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_cell": fam[top], "launch_groups": n, "avg_ms": t_ms / n,
+                    "share_of_step": t_ms / ms}
+    else:
+        roofline = None
+    B = bytes_per_cell_step(w, n_vc)
+    step_gbs = B * value / world / 1e9
+    roofline_step = {"bytes_per_cell_step": B, "vcycles_per_step": n_vc, "achieved": step_gbs, "unit": "GB/s per GPU",
+                     "frac_of_measured": step_gbs / peak_gbs, "frac_of_nominal_8TBs": step_gbs / 8000.0,
+                     "kernel_time_share": shares, "event_timed_ms_per_step": total_ms / args.steps}
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only) -------------------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        sample = workload(args.cpu_sample, 1)
+        v, cms, threads, cvc = cpu_reference_run(sample, args.cpu_steps, 1)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "%s, %d LFAM3 steps timed after 1 Euler + 1 warm-up step (%.0f ms/step, %.1f V-cycles/step); "
+                         "OpenMP -O3 -march=native build of the C restatement of the Fortran path, %s"
+                         % (sample["name"], args.cpu_steps, cms, cvc, cpu_model_string())}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": w["name"], "grid": [w["nx"], w["ny"], w["nz"]], "cells": cells,
+                       "parallelism": "z-slabs x%d" % world, "timestepping": "LFAM3",
+                       "l2": "inputs larger than L2 (every field is %.0f MB per GPU)" % (local_cells * 8 / 1e6),
+                       "vcycles_per_step": n_vc},
+            "roofline": roofline, "roofline_step": roofline_step, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": launches, "clocks": clocks}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="weak512")
+    ap.add_argument("--cpu-sample", default="rt128", help="bounded CPU sample of the workload")
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        print("note: fewer than 3 warm-up steps requested", file=sys.stderr)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -62,6 +62,13 @@ typedef struct ny_mg_stats {          /* MG_Stats, core/mgfor/mg_types.f90:45-48
     double reshist[32];               /* res before the 1st cycle, after cycle 1, ... */
 } ny_mg_stats;
 
+/* kernel families that ny_prof_* can time (CUDA events on the launching stream) */
+enum { NY_PROF_RHS_TRACER = 0, NY_PROF_RHS_MOMENTUM, NY_PROF_VORT_KE, NY_PROF_DIV, NY_PROF_GRADP,
+       NY_PROF_U_FROM_U, NY_PROF_TIMESCHEME, NY_PROF_MAXSPEED, NY_PROF_HALO,
+       NY_PROF_MG_SMOOTH_FINE, NY_PROF_MG_RESIDUAL_FINE, NY_PROF_MG_RESTRICT_FINE,
+       NY_PROF_MG_PROLONG_FINE, NY_PROF_MG_NORM, NY_PROF_MG_COARSE, NY_PROF_MG_EMBED,
+       NY_PROF_NTAGS };
+
 /* ---- context ---------------------------------------------------------------------- */
 int  ny_init(int device, ny_ctx** out);
 void ny_free(ny_ctx* ctx);
@@ -70,6 +77,14 @@ int  ny_version(void);
 /* number of kernel launches issued through this context since creation / last reset */
 long long ny_launch_count(ny_ctx* ctx);
 void ny_launch_count_reset(ny_ctx* ctx);
+
+/* Event timing of kernel families, used by bench.py for the per-kernel roofline.  mask: bit t
+ * enables family t.  ny_prof_collect synchronises the device, folds all finished event pairs
+ * into per-family totals and returns them: ms[t] (milliseconds) and n[t] (timed groups), arrays
+ * of NY_PROF_NTAGS entries.  ny_prof_start resets the totals. */
+int  ny_prof_start(ny_ctx* ctx, unsigned long long mask);
+int  ny_prof_collect(ny_ctx* ctx, double* ms_host, long long* n_host);
+const char* ny_prof_name(int tag);
 
 /* ---- f2py kernel replacements ------------------------------------------------------ */
 /* fortran_vorticity.vorticity x3 as driven by core/vorticity.py:7-34 (fparam = f*dx*dy, 0 = off) */

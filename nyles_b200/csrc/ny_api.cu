@@ -38,6 +38,8 @@ extern "C" int ny_init(int device, ny_ctx** out)
     ctx->scratch_doubles = 1 << 16;
     ctx->d_scratch = nullptr;
     ctx->h_pinned = nullptr;
+    ctx->prof_mask = 0;
+    for (int t = 0; t < NY_PROF_NTAGS; t++) { ctx->prof_ms[t] = 0.0; ctx->prof_n[t] = 0; }
     if (cudaMalloc(&ctx->d_scratch, ctx->scratch_doubles * sizeof(double)) != cudaSuccess ||
         cudaMallocHost(&ctx->h_pinned, 64 * sizeof(double)) != cudaSuccess) {
         ny_set_error("ny_init: scratch allocation failed");
@@ -53,8 +55,52 @@ extern "C" void ny_free(ny_ctx* ctx)
     if (!ctx) return;
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    for (ny_prof_rec& r : ctx->prof_recs) { cudaEventDestroy(r.t0); cudaEventDestroy(r.t1); }
+    for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
     delete ctx;
 }
 
 extern "C" long long ny_launch_count(ny_ctx* ctx) { return ctx ? ctx->launches : 0; }
 extern "C" void ny_launch_count_reset(ny_ctx* ctx) { if (ctx) ctx->launches = 0; }
+
+// ---- event profiling of kernel families ----------------------------------------------------
+static const char* const g_prof_names[NY_PROF_NTAGS] = {
+    "rhs_tracer", "rhs_momentum", "vorticity_ke", "div", "gradp", "U_from_u", "timescheme", "maxspeed",
+    "halo", "mg_smooth_fine", "mg_residual_fine", "mg_restrict_fine", "mg_prolong_fine", "mg_norm",
+    "mg_coarse_levels", "mg_embed_extract"};
+
+extern "C" const char* ny_prof_name(int tag)
+{
+    return (tag >= 0 && tag < NY_PROF_NTAGS) ? g_prof_names[tag] : "";
+}
+
+extern "C" int ny_prof_collect(ny_ctx* ctx, double* ms_host, long long* n_host)
+{
+    NY_REQUIRE(ctx, "null argument");
+    NY_CUDA(cudaDeviceSynchronize());
+    for (ny_prof_rec& r : ctx->prof_recs) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.t0, r.t1) == cudaSuccess) {
+            ctx->prof_ms[r.tag] += ms;
+            ctx->prof_n[r.tag] += 1;
+        }
+        ctx->prof_pool.push_back(r.t0);
+        ctx->prof_pool.push_back(r.t1);
+    }
+    ctx->prof_recs.clear();
+    for (int t = 0; t < NY_PROF_NTAGS; t++) {
+        if (ms_host) ms_host[t] = ctx->prof_ms[t];
+        if (n_host) n_host[t] = ctx->prof_n[t];
+    }
+    return NY_OK;
+}
+
+extern "C" int ny_prof_start(ny_ctx* ctx, unsigned long long mask)
+{
+    NY_REQUIRE(ctx, "null argument");
+    int r = ny_prof_collect(ctx, nullptr, nullptr);
+    if (r != NY_OK) return r;
+    for (int t = 0; t < NY_PROF_NTAGS; t++) { ctx->prof_ms[t] = 0.0; ctx->prof_n[t] = 0; }
+    ctx->prof_mask = mask;
+    return NY_OK;
+}

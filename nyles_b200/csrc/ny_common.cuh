@@ -6,6 +6,11 @@
 #include <cstring>
 #include "../../include/nyles_b200.h"
 
+#include <vector>
+
+// kernel families that can be timed individually with CUDA events (ny_prof_*), see nyles_b200.h
+struct ny_prof_rec { int tag; cudaEvent_t t0, t1; };
+
 struct ny_ctx {
     int device;
     int num_sms;
@@ -13,6 +18,30 @@ struct ny_ctx {
     double* d_scratch;        // reduction partials (device)
     size_t scratch_doubles;
     double* h_pinned;         // small pinned mailbox for scalars
+    // event profiling of tagged launch groups
+    unsigned long long prof_mask;
+    std::vector<ny_prof_rec> prof_recs;
+    std::vector<cudaEvent_t> prof_pool;
+    double prof_ms[NY_PROF_NTAGS];
+    long long prof_n[NY_PROF_NTAGS];
+};
+
+// RAII: brackets the launches issued in its scope with two events on `st` when the tag is enabled
+struct ny_prof_scope {
+    ny_ctx* ctx; int slot; cudaStream_t st;
+    ny_prof_scope(ny_ctx* c, int tag, cudaStream_t s) : ctx(c), slot(-1), st(s)
+    {
+        if (!(c->prof_mask >> tag & 1ull)) return;
+        ny_prof_rec r; r.tag = tag;
+        for (cudaEvent_t* e : {&r.t0, &r.t1}) {
+            if (!c->prof_pool.empty()) { *e = c->prof_pool.back(); c->prof_pool.pop_back(); }
+            else if (cudaEventCreate(e) != cudaSuccess) return;
+        }
+        cudaEventRecord(r.t0, s);
+        slot = (int)c->prof_recs.size();
+        c->prof_recs.push_back(r);
+    }
+    ~ny_prof_scope() { if (slot >= 0) cudaEventRecord(ctx->prof_recs[slot].t1, st); }
 };
 
 void ny_set_error(const char* fmt, ...);

@@ -202,6 +202,7 @@ extern "C" int ny_vorticity(ny_ctx* ctx, const double* ux, const double* uy, con
 {
     NY_REQUIRE(ctx && ux && uy && uz && wx && wy && wz, "null argument");
     ny_grid3 g = ny_cells_launch(e.nz, e.ny, e.nx);
+    ny_prof_scope ps(ctx, NY_PROF_VORT_KE, ny_stream(stream));
     k_vorticity<<<g.grid, g.block, 0, ny_stream(stream)>>>(ux, uy, uz, wx, wy, wz, fparam, make_ext(e));
     NY_CHECK_LAUNCH(ctx);
     return NY_OK;
@@ -213,6 +214,7 @@ extern "C" int ny_kin(ny_ctx* ctx, const double* ux, const double* uy, const dou
     NY_REQUIRE(ctx && ux && uy && uz && ke, "null argument");
     ny_grid3 g = ny_cells_launch(e.nz, e.ny, e.nx);
     // fortran_kinenergy.f90:43,48: cff2 = 0.5*ds2; ke += cff2*0.5*(...)
+    ny_prof_scope ps(ctx, NY_PROF_VORT_KE, ny_stream(stream));
     k_kin<<<g.grid, g.block, 0, ny_stream(stream)>>>(ux, uy, uz, ke, (0.5 * idx2) * 0.5, (0.5 * idy2) * 0.5,
                                                       (0.5 * idz2) * 0.5, make_ext(e));
     NY_CHECK_LAUNCH(ctx);
@@ -224,6 +226,7 @@ extern "C" int ny_div(ny_ctx* ctx, const double* Ux, const double* Uy, const dou
 {
     NY_REQUIRE(ctx && Ux && Uy && Uz && div, "null argument");
     ny_grid3 g = ny_cells_launch(e.nz, e.ny, e.nx);
+    ny_prof_scope ps(ctx, NY_PROF_DIV, ny_stream(stream));
     k_div<<<g.grid, g.block, 0, ny_stream(stream)>>>(Ux, Uy, Uz, div, make_ext(e));
     NY_CHECK_LAUNCH(ctx);
     return NY_OK;
@@ -233,6 +236,7 @@ extern "C" int ny_gradp(ny_ctx* ctx, const double* p, double* ux, double* uy, do
 {
     NY_REQUIRE(ctx && p && ux && uy && uz, "null argument");
     ny_grid3 g = ny_cells_launch(e.nz, e.ny, e.nx);
+    ny_prof_scope ps(ctx, NY_PROF_GRADP, ny_stream(stream));
     k_gradp<<<g.grid, g.block, 0, ny_stream(stream)>>>(p, ux, uy, uz, make_ext(e));
     NY_CHECK_LAUNCH(ctx);
     return NY_OK;
@@ -244,12 +248,14 @@ extern "C" int ny_U_from_u(ny_ctx* ctx, const double* ux, const double* uy, cons
 {
     NY_REQUIRE(ctx && ux && uy && uz && Ux && Uy && Uz, "null argument");
     long long n = (long long)e.nz * e.ny * e.nx;
+    ny_prof_scope ps(ctx, NY_PROF_U_FROM_U, ny_stream(stream));
     k_scale3<<<ts_blocks(ctx, n), 256, 0, ny_stream(stream)>>>(ux, uy, uz, Ux, Uy, Uz, idx2, idy2, idz2, n);
     NY_CHECK_LAUNCH(ctx);
     return NY_OK;
 }
 
 #define TS_LAUNCH(MODE, ...)                                                                     \
+    ny_prof_scope ps(ctx, NY_PROF_TIMESCHEME, ny_stream(stream));                                \
     k_ts<MODE><<<ts_blocks(ctx, n), 256, 0, ny_stream(stream)>>>(__VA_ARGS__);                   \
     NY_CHECK_LAUNCH(ctx);                                                                        \
     return NY_OK;
@@ -297,6 +303,7 @@ extern "C" int ny_max_speed2(ny_ctx* ctx, const double* Ux, const double* Uy, co
     int nb = ts_blocks(ctx, n);
     NY_REQUIRE((size_t)nb + 1 <= ctx->scratch_doubles, "scratch too small");
     cudaStream_t st = ny_stream(stream);
+    ny_prof_scope ps(ctx, NY_PROF_MAXSPEED, ny_stream(stream));
     k_maxspeed_partial<<<nb, 256, 0, st>>>(Ux, Uy, Uz, n, ctx->d_scratch + 1);
     NY_CHECK_LAUNCH(ctx);
     k_max_final<<<1, 1, 0, st>>>(ctx->d_scratch + 1, nb, ctx->d_scratch);
@@ -322,6 +329,7 @@ extern "C" int ny_halo_fill_self(ny_ctx* ctx, double* f, ny_ext e, int nh, const
     }
     g.nh = nh;
     ny_grid3 l = ny_cells_launch(e.nz, e.ny, e.nx);
+    ny_prof_scope ps(ctx, NY_PROF_HALO, ny_stream(stream));
     k_halo_self<<<l.grid, l.block, 0, ny_stream(stream)>>>(f, g);
     NY_CHECK_LAUNCH(ctx);
     return NY_OK;

@@ -316,6 +316,7 @@ int smooth(ny_mg* mg, cudaStream_t st, int lev)
     Level& L = mg->lev[lev - 1];
     const int nh = mg->nh;
     const double omega = mg->omega, cff1 = 1.0 - omega;
+    ny_prof_scope ps(mg->ctx, lev == 1 ? NY_PROF_MG_SMOOTH_FINE : NY_PROF_MG_COARSE, st);
     dim3 b(32, 4, 2);
     k_sweep<<<box_grid(L.nx + 2, L.ny + 2, L.nz - 2 * nh + 2, b), b, 0, st>>>(
         L.x, L.y, L.b, L.idiag, omega, cff1, L, nh, 0, L.nx + 1, 0, L.ny + 1, nh, L.nz + 1 - nh);
@@ -329,6 +330,7 @@ int smooth(ny_mg* mg, cudaStream_t st, int lev)
 int residual(ny_mg* mg, cudaStream_t st, int lev)
 {
     Level& L = mg->lev[lev - 1];
+    ny_prof_scope ps(mg->ctx, lev == 1 ? NY_PROF_MG_RESIDUAL_FINE : NY_PROF_MG_COARSE, st);
     dim3 b(32, 4, 2);
     k_residual<<<box_grid(L.nx, L.ny, L.nz - 2 * mg->nh, b), b, 0, st>>>(L.x, L.b, L.r, L.msk, L.diag, L, mg->nh);
     LAUNCH_OK(mg);
@@ -338,6 +340,7 @@ int residual(ny_mg* mg, cudaStream_t st, int lev)
 int restriction(ny_mg* mg, cudaStream_t st, int lev, bool from_b)
 {
     Level &F = mg->lev[lev - 1], &C = mg->lev[lev];
+    ny_prof_scope ps(mg->ctx, lev == 1 ? NY_PROF_MG_RESTRICT_FINE : NY_PROF_MG_COARSE, st);
     dim3 b(32, 4, 2);
     k_restrict<<<box_grid(C.nx, C.ny, C.nz - 2 * mg->nh, b), b, 0, st>>>(from_b ? F.b : F.r, C.b, C.Rcoef, F, C, mg->nh);
     LAUNCH_OK(mg);
@@ -348,6 +351,7 @@ int restriction(ny_mg* mg, cudaStream_t st, int lev, bool from_b)
 int prolongation(ny_mg* mg, cudaStream_t st, int lev)
 {
     Level &F = mg->lev[lev - 1], &C = mg->lev[lev];
+    ny_prof_scope ps(mg->ctx, lev == 1 ? NY_PROF_MG_PROLONG_FINE : NY_PROF_MG_COARSE, st);
     dim3 b(32, 4, 2);
     k_prolong<<<box_grid(F.nx, F.ny, F.nz - 2 * mg->nh, b), b, 0, st>>>(F.x, C.x, F.Pcoef, F, C, mg->nh);
     LAUNCH_OK(mg);
@@ -358,6 +362,7 @@ int prolongation(ny_mg* mg, cudaStream_t st, int lev)
 int norm_async(ny_mg* mg, cudaStream_t st, const double* v, int slot)
 {
     Level& L = mg->lev[0];
+    ny_prof_scope ps(mg->ctx, NY_PROF_MG_NORM, st);
     k_norm_partial<<<NORM_BLOCKS, 256, 0, st>>>(L.msk, v, L, mg->nh, mg->d_red + 2);
     LAUNCH_OK(mg);
     k_norm_final<<<1, 256, 0, st>>>(mg->d_red + 2, NORM_BLOCKS, mg->d_red + slot);
@@ -618,9 +623,13 @@ extern "C" int ny_mg_solve_directly(ny_mg* mg, double* p, const double* div, ny_
                lo[0] >= 0 && lo[1] >= 0 && lo[2] >= 0, "model array does not fit the multigrid array");
     cudaStream_t st = ny_stream(stream);
     ny_grid3 g = ny_cells_launch(e.nz, e.ny, e.nx);
-    k_embed<<<g.grid, g.block, 0, st>>>(L.b, div, L, e.nz, e.ny, e.nx, lo[0], lo[1], lo[2]);
-    LAUNCH_OK(mg);
+    {
+        ny_prof_scope ps(mg->ctx, NY_PROF_MG_EMBED, st);
+        k_embed<<<g.grid, g.block, 0, st>>>(L.b, div, L, e.nz, e.ny, e.nx, lo[0], lo[1], lo[2]);
+        LAUNCH_OK(mg);
+    }
     TRY(ny_mg_solve(mg, stats, stream));
+    ny_prof_scope ps(mg->ctx, NY_PROF_MG_EMBED, st);
     k_extract<<<g.grid, g.block, 0, st>>>(L.x, p, L, e.nz, e.ny, e.nx, lo[0], lo[1], lo[2], scale);
     LAUNCH_OK(mg);
     return NY_OK;

@@ -151,6 +151,7 @@ extern "C" int ny_upwind(ny_ctx* ctx, const double* trac, const double* Ux, cons
     NY_REQUIRE(ctx && trac && Ux && Uy && Uz && dtrac, "null argument");
     NY_REQUIRE(ext_ok(e), "every extent must be >= 5 (flux1d closure, core/weno.f90:106-153)");
     ny_grid3 g = ny_cells_launch(e.nz, e.ny, e.nx);
+    ny_prof_scope ps(ctx, NY_PROF_RHS_TRACER, ny_stream(stream));
     k_upwind<false><<<g.grid, g.block, 0, ny_stream(stream)>>>(trac, Ux, Uy, Uz, dtrac, 0.0, 0.0, 0.0, make_ext(e));
     NY_CHECK_LAUNCH(ctx);
     return NY_OK;
@@ -162,6 +163,7 @@ extern "C" int ny_upwind_diff(ny_ctx* ctx, const double* trac, const double* Ux,
     NY_REQUIRE(ctx && trac && Ux && Uy && Uz && dtrac, "null argument");
     NY_REQUIRE(ext_ok(e), "every extent must be >= 5 (flux1d closure, core/weno.f90:106-153)");
     ny_grid3 g = ny_cells_launch(e.nz, e.ny, e.nx);
+    ny_prof_scope ps(ctx, NY_PROF_RHS_TRACER, ny_stream(stream));
     k_upwind<true><<<g.grid, g.block, 0, ny_stream(stream)>>>(trac, Ux, Uy, Uz, dtrac, cx, cy, cz, make_ext(e));
     NY_CHECK_LAUNCH(ctx);
     return NY_OK;
@@ -174,6 +176,7 @@ extern "C" int ny_vortex_force(ny_ctx* ctx, const double* Ux, const double* Uy, 
     NY_REQUIRE(ctx && Ux && Uy && Uz && wx && wy && wz && dux && duy && duz, "null argument");
     NY_REQUIRE(ext_ok(e), "every extent must be >= 5 (flux1d closure, core/weno.f90:106-153)");
     ny_grid3 g = ny_cells_launch(e.nz, e.ny, e.nx);
+    ny_prof_scope ps(ctx, NY_PROF_RHS_MOMENTUM, ny_stream(stream));
     k_momentum<true, true, false><<<g.grid, g.block, 0, ny_stream(stream)>>>(
         Ux, Uy, Uz, wx, wy, wz, nullptr, nullptr, dux, duy, duz, 0.0, 0, make_ext(e));
     NY_CHECK_LAUNCH(ctx);
@@ -185,6 +188,7 @@ extern "C" int ny_bernoulli(ny_ctx* ctx, const double* ke, const double* b, doub
 {
     NY_REQUIRE(ctx && ke && dux && duy && duz && (euler || b), "null argument");
     ny_grid3 g = ny_cells_launch(e.nz, e.ny, e.nx);
+    ny_prof_scope ps(ctx, NY_PROF_RHS_MOMENTUM, ny_stream(stream));
     k_momentum<true, false, true><<<g.grid, g.block, 0, ny_stream(stream)>>>(
         nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, ke, b, dux, duy, duz, 0.5 * dz, euler ? 0 : 1, make_ext(e));
     NY_CHECK_LAUNCH(ctx);
@@ -214,9 +218,11 @@ extern "C" int ny_rhs(ny_ctx* ctx, const double* b, const double* Ux, const doub
     ny_grid3 g = ny_cells_launch(e.nz, e.ny, e.nx);
     Ext x = make_ext(e);
     if (!euler) {
+        ny_prof_scope ps(ctx, NY_PROF_RHS_TRACER, ny_stream(stream));
         k_upwind<false><<<g.grid, g.block, 0, ny_stream(stream)>>>(b, Ux, Uy, Uz, db, 0.0, 0.0, 0.0, x);
         NY_CHECK_LAUNCH(ctx);
     }
+    ny_prof_scope ps(ctx, NY_PROF_RHS_MOMENTUM, ny_stream(stream));
     if (linear)
         k_momentum<false, false, true><<<g.grid, g.block, 0, ny_stream(stream)>>>(
             Ux, Uy, Uz, wx, wy, wz, ke, b, dux, duy, duz, 0.5 * dz, euler ? 0 : 1, x);

@@ -42,6 +42,9 @@ _PROTOS = {
     "ny_version": ([], _I),
     "ny_launch_count": ([_P], _LL),
     "ny_launch_count_reset": ([_P], None),
+    "ny_prof_start": ([_P, C.c_ulonglong], _I),
+    "ny_prof_collect": ([_P, C.POINTER(_D), C.POINTER(_LL)], _I),
+    "ny_prof_name": ([_I], C.c_char_p),
     "ny_vorticity": ([_P] + [_P] * 6 + [ny_ext, _D, _P], _I),
     "ny_upwind": ([_P] + [_P] * 5 + [ny_ext, _P], _I),
     "ny_upwind_diff": ([_P] + [_P] * 5 + [_D, _D, _D, ny_ext, _P], _I),
@@ -139,3 +142,19 @@ def launch_count():
 def launch_count_reset():
     for h in _ctx.values():
         load().ny_launch_count_reset(h)
+
+
+NY_PROF_NTAGS = 16
+
+
+def prof_start(mask=(1 << NY_PROF_NTAGS) - 1, device=None):
+    """Time the enabled kernel families with CUDA events on their launching stream."""
+    check(load().ny_prof_start(context(device), mask))
+
+
+def prof_collect(device=None):
+    """{family: (total_ms, groups)} since prof_start (synchronises the device)."""
+    ms = (_D * NY_PROF_NTAGS)()
+    n = (_LL * NY_PROF_NTAGS)()
+    check(load().ny_prof_collect(context(device), ms, n))
+    return {load().ny_prof_name(t).decode(): (ms[t], n[t]) for t in range(NY_PROF_NTAGS)}

@@ -126,5 +126,29 @@ class Nyles(object):
             return self.dt_max
         return min(self.cfl / U_max, self.dt_max)
 
+    # ------------------------------------------------------------------ host-buffer interface
+    def prognostic_tensors(self):
+        st = self.model.state
+        return [st.get(name).tensor for name in st.get_prognostic_scalars()]
+
+    def allocate_host_state(self):
+        """Pinned host arrays (canonical (k,j,i) order) for the prognostic fields b, u_i, u_j, u_k, ...:
+        the layout in which a caller of the reference's f2py/ctypes boundary holds its NumPy state."""
+        return [torch.empty(t.shape, dtype=t.dtype, device="cpu", pin_memory=True) for t in self.prognostic_tensors()]
+
+    def step_host(self, t, host_state):
+        """One model step on HOST buffers: upload the prognostic state, compute dt, step, download the
+        new state into the same buffers.  Returns dt.  This is the call whose cost bench.py reports as
+        `e2e`: what a user pays who keeps the state in host memory, as the reference does."""
+        dev = self.prognostic_tensors()
+        for h, d in zip(host_state, dev):
+            d.copy_(h, non_blocking=True)
+        dt = self.compute_dt()
+        self.model.forward(t, dt)
+        for h, d in zip(host_state, dev):
+            h.copy_(d, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return dt
+
     def banner(self):
         print("nyles_b200: B200-native LES time step with the Nyles API")
