@@ -31,6 +31,7 @@ extern "C" {
 
 typedef struct ny_ctx ny_ctx;
 typedef struct ny_mg ny_mg;
+typedef struct ny_comm ny_comm;     /* slab communicator: NCCL over NVLink, one rank per GPU */
 
 typedef struct ny_ext { int nz, ny, nx; } ny_ext;
 
@@ -162,11 +163,42 @@ int ny_max_speed2(ny_ctx*, const double* Ux, const double* Uy, const double* Uz,
  * per[3] = {z,y,x}: nonzero if that axis carries halos that wrap onto this same array. */
 int ny_halo_fill_self(ny_ctx*, double* f, ny_ext e, int nh, const int per[3], void* stream);
 
+/* ---- slab communicator (replaces mpi4py / mpi_f08: core/mpi/halo.py, mpitools.py, mgfor/mod_halo.f90,
+ * mod_gluesplit.f90).  Ranks are ordered along z; rank r owns the r-th slab.  NCCL is looked up at
+ * run time (dlsym), so single-GPU users do not need it.  Bootstrap: rank 0 calls ny_comm_unique_id,
+ * the 128 bytes are broadcast by the host program (torch.distributed, MPI, a file ...), every rank
+ * calls ny_comm_init. */
+int  ny_comm_unique_id(char* id128);
+int  ny_comm_init(ny_ctx* ctx, int nranks, int rank, const char* id128, ny_comm** out);
+void ny_comm_free(ny_comm* comm);
+int  ny_comm_size(ny_comm* comm);
+int  ny_comm_rank(ny_comm* comm);
+/* sum (op_max = 0) or max (op_max != 0) of n <= 8 host doubles over all ranks; synchronises `stream`
+ * (core/mpi/mpitools.py:28-32) */
+int  ny_comm_allreduce_host(ny_comm* comm, double* values_host, int n, int op_max, void* stream);
+/* Halo.fill for z slabs (core/mpi/halo.py:140-178): exchange the nh-plane z faces of `nfields`
+ * arrays (fields_host: HOST array of device pointers) with ranks `below` / `above` (-1 = wall or
+ * none), then wrap periodic x / y halos locally over all planes. */
+int  ny_halo_exchange(ny_ctx* ctx, ny_comm* comm, double* const* fields_host, int nfields, ny_ext e, int nh,
+                      int below, int above, int yper, int xper, void* stream);
+
 /* ---- multigrid (libmgmod64.so replacement) --------------------------------------------- */
 /* get_ptrmg(npx=1,npy=1,nx,ny,nz,vertices=F,short=F,is3d=T,topology), mg_setup.f90:318-437 */
 int  ny_mg_create(ny_ctx*, int nx, int ny, int nz, int topology, ny_mg** out);
+/* the same solver on z slabs, one rank per GPU: nx, ny, nz_global are GLOBAL extents, rank r of
+ * `comm` owns planes [r*nz_global/P, (r+1)*nz_global/P).  Level arrays are local slabs padded by nh
+ * (z halos filled from the neighbours through NCCL); small levels are gathered and solved
+ * redundantly (mg_setup.f90:275-293).  Collective: every rank must make the same calls. */
+int  ny_mg_create_slab(ny_ctx*, ny_comm* comm, int nx, int ny, int nz_global, int topology, ny_mg** out);
 void ny_mg_destroy(ny_mg*);
 int  ny_mg_nlevels(ny_mg*);
+/* 1 if the mask is the default box, so that the fused analytic-coefficient kernels are in use */
+int  ny_mg_is_box(ny_mg*);
+/* on = 0 forces the generic kernels that read the coefficient arrays (one rank only; used by the
+ * tests to cross-check the two paths), on = 1 re-verifies and re-enables the box kernels */
+int  ny_mg_set_fast_path(ny_mg*, int on);
+/* 1-based index of the first level that is replicated on every rank (1 on a single rank) */
+int  ny_mg_first_gathered_level(ny_mg*);
 /* get_pyshape: shape[0..2] = (nz+2nh, ny+2nh, nx+2nh) of level lev (1-based), numpy order */
 int  ny_mg_shape(ny_mg*, int lev, int shape[3]);
 /* MG_Param fields that matter (mg_types.f90:15-26); defaults maxite=20, tol=1e-6, omega=0.9 */

@@ -1,0 +1,19 @@
+// Internal interface of the slab communicator (ny_comm.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <nccl.h>
+#include "../../include/nyles_b200.h"
+
+struct ny_ctx;
+struct ny_comm {
+    ny_ctx* ctx;
+    int nranks, rank;
+    ncclComm_t nccl;
+    double* d_red;            // small device mailbox for host-value reductions
+};
+
+// all return NY_OK or a negative ny_status; no-ops when c is null or has a single rank
+int ny_comm_allreduce(ny_comm* c, double* d_buf, int n, int op_max, cudaStream_t st);
+int ny_comm_allgather_inplace(ny_comm* c, double* d_recv, size_t count_per_rank, cudaStream_t st);
+int ny_comm_exchange_z(ny_comm* c, double* const* arrays, int nf, size_t plane, int lo, int nint, int nh,
+                       int below, int above, cudaStream_t st);

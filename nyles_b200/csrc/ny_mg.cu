@@ -6,47 +6,107 @@
 //   smoother           basicoperators.f90:363-400 (two damped-Jacobi sweeps, omega = 0.9)
 //   residual           basicoperators.f90:300-323  restriction  :32-60   prolongation :173-231
 //   norm               basicoperators.f90:422-440  V-cycle / solve  solvers.f90:8-55
-//   halo fill          mod_halo.f90:235-262 (one process: periodic self exchange)
+//   halo fill          mod_halo.f90:200-262
 // Level arrays are (nz+2nh, ny+2nh, nx+2nh), i fastest, exactly the reference's padded layout.
 // Arithmetic: source order, no FMA (-fmad=false) -> bit-identical to the oracle except for the
 // summation order of the two norms, which only feed the stopping test.
+//
+// Two code paths, both CUDA:
+//   * generic : one kernel per Fortran loop nest, coefficient arrays (msk, diag, idiag, Rcoef,
+//               Pcoef) read from memory.  Used for the one-time operator setup (which follows
+//               operators.f90:299-457 literally) and whenever the mask is not the default box.
+//   * box     : the hot path.  For box domains every coefficient is a function of the cell
+//               position, so nothing but x and b is read: the two Jacobi sweeps are fused in one
+//               pass (k-streaming tiles, z neighbours in registers, in-plane neighbours through
+//               shared memory), residual+restriction and residual+norm never materialise r.
+//               The analytic coefficients are verified against the arrays at creation.
+// Multi-GPU: z slabs (one rank per GPU).  Distributed levels exchange 3-plane z faces through
+// NCCL; once a level is small it is gathered (ncclAllGather) and all coarser levels are solved
+// redundantly on every rank (mirror of mg_setup.f90:275-293 / mod_gluesplit.f90).
 #include "ny_common.cuh"
+#include "ny_comm.cuh"
 
 namespace {
 
 constexpr int MAXLEV = 50;
-constexpr int NORM_BLOCKS = 1184;          // 8 x 148 SMs
+constexpr int NH = 3;
+constexpr int MAX_PARTIALS = 1 << 15;
 
 struct Level {
-    int nx, ny, nz;                        // nz includes the 2*nh halo planes
+    int nx, ny, nz;                        // nz = local planes including the 2*nh halo planes
     long long sj, sk;
     size_t n;
+    int zlo, zhi;                          // the domain continues below / above the local array (periodic or slab neighbour)
+    int gathered;                          // replicated on every rank (always true on one rank)
     double *x, *b, *r, *y, *diag, *idiag, *Rcoef, *Pcoef, *msk;
+};
+
+// what the box kernels need to know about a level array (or a window of one)
+struct Box {
+    int nx, ny, nz;                        // interior extents in x, y; padded plane count in z
+    long long sj, sk;
+    int xper, yper, zlo, zhi;
 };
 
 }  // namespace
 
 struct ny_mg {
     ny_ctx* ctx;
+    ny_comm* comm;
+    int nranks, rank;
     int nlevels, nh, topology, maxite;
     int xper, yper, zper;
+    int box;                               // default mask: analytic coefficients are valid
+    int glev;                              // first gathered level (0-based); 0 on one rank
+    int below, above;                      // slab neighbours (-1: none)
     double tol, omega;
     Level lev[MAXLEV];
     double* tmp;                           // staging for overlapping halo sections
     size_t tmp_doubles;
-    double* d_red;                         // NORM_BLOCKS partials + 2 results
+    double* d_red;                         // MAX_PARTIALS partials + 4 results
+    int* d_flag;
 };
 
 namespace {
 
-// Fortran indices (i in 1-nh..nx+nh, j likewise, k in 1..nz) -> linear offset
 __host__ __device__ inline long long IX(const Level& L, int nh, int i, int j, int k)
-{
+{   // Fortran indices (i in 1-nh..nx+nh, j likewise, k in 1..nz) -> linear offset
     return (long long)(k - 1) * L.sk + (long long)(j - 1 + nh) * L.sj + (i - 1 + nh);
 }
 
-// ---- stencil kernels ---------------------------------------------------------------------
-// one damped-Jacobi sweep over the Fortran index box [i0,i1]x[j0,j1]x[k0,k1]
+inline Box box_of(const ny_mg* mg, const Level& L)
+{
+    Box g; g.nx = L.nx; g.ny = L.ny; g.nz = L.nz; g.sj = L.sj; g.sk = L.sk;
+    g.xper = mg->xper; g.yper = mg->yper; g.zlo = L.zlo; g.zhi = L.zhi;
+    return g;
+}
+
+// ---- analytic coefficients of a box domain (array indices, 0-based) --------------------------
+__device__ __forceinline__ bool in_x(const Box& g, int ai) { return g.xper || (ai >= NH && ai < g.nx + NH); }
+__device__ __forceinline__ bool in_y(const Box& g, int aj) { return g.yper || (aj >= NH && aj < g.ny + NH); }
+__device__ __forceinline__ bool in_z(const Box& g, int ak) { return (ak >= NH || g.zlo) && (ak < g.nz - NH || g.zhi); }
+// number of in-domain neighbours in the plane (the x,y part of diag = msk * sum_6 msk), or a large
+// negative number if the column itself is outside the domain
+__device__ __forceinline__ int cnt_xy(const Box& g, int ai, int aj)
+{
+    if (!(in_x(g, ai) && in_y(g, aj))) return -100;
+    return (int)in_x(g, ai - 1) + (int)in_x(g, ai + 1) + (int)in_y(g, aj - 1) + (int)in_y(g, aj + 1);
+}
+__device__ __forceinline__ int cnt_z(const Box& g, int ak)
+{
+    if (!in_z(g, ak)) return -100;
+    return (int)in_z(g, ak - 1) + (int)in_z(g, ak + 1);
+}
+// Pcoef of a fine cell whose three "other" coarse neighbours have e in-domain flags set
+// (operators.f90:395-424 evaluated for the default mask: 1 / ((3+ex)(3+ey)(3+ez)))
+__device__ __forceinline__ double pcoef_of(int e)
+{
+    return e == 3 ? 1.0 / 64.0 : (e == 2 ? 1.0 / 48.0 : (e == 1 ? 1.0 / 36.0 : 1.0 / 27.0));
+}
+
+// =================================================================================================
+//  generic kernels (coefficient arrays)
+// =================================================================================================
 __global__ void __launch_bounds__(256)
 k_sweep(const double* __restrict__ src, double* __restrict__ dst, const double* __restrict__ b,
         const double* __restrict__ idiag, double omega, double cff1, Level L, int nh,
@@ -74,6 +134,7 @@ k_residual(const double* __restrict__ x, const double* __restrict__ b, double* _
     r[c] = msk[c] * (b[c] + diag[c] * x[c] - s);
 }
 
+// coef == nullptr: box domain, Rcoef = 0.5 on every interior coarse cell
 __global__ void __launch_bounds__(256)
 k_restrict(const double* __restrict__ xf, double* __restrict__ xc, const double* __restrict__ coef,
            Level F, Level C, int nh)
@@ -87,18 +148,18 @@ k_restrict(const double* __restrict__ xf, double* __restrict__ xc, const double*
     double s = xf[f] + xf[f + 1] + xf[f + F.sj] + xf[f + F.sj + 1]
              + xf[f + F.sk] + xf[f + F.sk + 1] + xf[f + F.sk + F.sj] + xf[f + F.sk + F.sj + 1];
     long long c = IX(C, nh, ic, jc, kc);
-    xc[c] = coef[c] * s;
+    xc[c] = (coef ? coef[c] : 0.5) * s;
 }
 
-// one thread per fine cell; (i,j) parity picks the coarse neighbours, k parity picks plane a or c
+// one thread per fine cell; (i,j) parity picks the coarse neighbours, k parity picks plane a or c.
+// coef == nullptr: box domain, analytic Pcoef.
 __global__ void __launch_bounds__(256)
 k_prolong(double* __restrict__ xf, const double* __restrict__ xc, const double* __restrict__ coef,
-          Level F, Level C, int nh)
+          Level F, Level C, Box gc, int nh)
 {
     int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;
     int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
     int k = 1 + nh + blockIdx.z * blockDim.z + threadIdx.z;
-    // source loops run over 2x2x2 fine blocks; extents are even on every level that is refined
     if (i > F.nx || j > F.ny || k > F.nz - nh) return;
     int ic = (i + 1) / 2, jc = (j + 1) / 2;
     int di = (i & 1) ? -1 : 1, dj = (j & 1) ? -1 : 1;
@@ -111,7 +172,10 @@ k_prolong(double* __restrict__ xf, const double* __restrict__ xc, const double* 
     double pb = 9 * xc[cb] + 3 * xc[cb + ox] + 3 * xc[cb + oy] + xc[cb + ox + oy];
     double po = 9 * xc[co] + 3 * xc[co + ox] + 3 * xc[co + oy] + xc[co + ox + oy];
     long long f = IX(F, nh, i, j, k);
-    xf[f] = xf[f] + coef[f] * (3 * pb + po);
+    double cf;
+    if (coef) cf = coef[f];
+    else cf = pcoef_of((int)in_x(gc, ic + di - 1 + nh) + (int)in_y(gc, jc + dj - 1 + nh) + (int)in_z(gc, ko - 1));
+    xf[f] = xf[f] + cf * (3 * pb + po);
 }
 
 // sum(msk * x*x) over the interior: fixed grid-stride order => deterministic
@@ -143,7 +207,7 @@ k_norm_partial(const double* __restrict__ msk, const double* __restrict__ x, Lev
     }
 }
 __global__ void __launch_bounds__(256)
-k_norm_final(const double* __restrict__ partial, int nb, double* __restrict__ out)
+k_sum_final(const double* __restrict__ partial, int nb, double* __restrict__ out)
 {
     __shared__ double sh[256];
     double acc = 0.0;
@@ -172,6 +236,44 @@ k_box_copy(const double* src, double* dst, Level L, int nh,
         double v = src_packed ? src[t] : src[IX(L, nh, si0 + i, sj0 + j, sk0 + k)];
         if (dst_packed) dst[t] = v; else dst[IX(L, nh, di0 + i, dj0 + j, dk0 + k)] = v;
     }
+}
+
+// Whole periodic halo fill in one launch, valid when every wrapped axis is at least nh wide (then
+// the statement sequence of mod_halo.f90:235-262 equals the rule below).  wz: wrap z too.
+// Threads: segment 0 = the 2*nh z-halo planes, segment 1 = y-halo rows of the other planes,
+// segment 2 = x-halo columns of the remaining rows.  x and y sections of the Fortran cover all k,
+// the corner sections exist only when both x and y are periodic, the z sections copy full planes.
+__global__ void __launch_bounds__(256)
+k_fill_periodic(double* __restrict__ a, int nx, int ny, int nz, long long sj, long long sk,
+                int xper, int yper, int wz, long long n0, long long n1, long long n2)
+{
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int ai, aj, ak;
+    const int tx = nx + 2 * NH, ty = ny + 2 * NH;
+    if (t < n0) {
+        ai = (int)(t % tx); long long q = t / tx; aj = (int)(q % ty); int p = (int)(q / ty);
+        ak = p < NH ? p : nz - 2 * NH + p;
+    } else if (t < n0 + n1) {
+        t -= n0;
+        ai = (int)(t % tx); long long q = t / tx; int r = (int)(q % (2 * NH)); ak = NH + (int)(q / (2 * NH));
+        aj = r < NH ? r : ny + r;
+    } else if (t < n0 + n1 + n2) {
+        t -= n0 + n1;
+        int c = (int)(t % (2 * NH)); long long q = t / (2 * NH); aj = NH + (int)(q % ny); ak = NH + (int)(q / ny);
+        ai = c < NH ? c : nx + c;
+    } else return;
+    const bool hx = ai < NH || ai >= nx + NH, hy = aj < NH || aj >= ny + NH, hz = ak < NH || ak >= nz - NH;
+    int si = ai, sjj = aj, skk = ak;
+    if (hz && wz) skk = ak < NH ? ak + (nz - 2 * NH) : ak - (nz - 2 * NH);
+    if (hx && hy) {
+        if (xper && yper) { si = ai < NH ? ai + nx : ai - nx; sjj = aj < NH ? aj + ny : aj - ny; }
+    } else if (hx) {
+        if (xper) si = ai < NH ? ai + nx : ai - nx;
+    } else if (hy) {
+        if (yper) sjj = aj < NH ? aj + ny : aj - ny;
+    }
+    if (si == ai && sjj == aj && skk == ak) return;
+    a[(long long)ak * sk + (long long)aj * sj + ai] = a[(long long)skk * sk + (long long)sjj * sj + si];
 }
 
 // ---- elementwise helpers for the one-time operator setup -------------------------------------
@@ -215,6 +317,38 @@ k_apply_default_msk(double* __restrict__ msk, Level L, int nh, int xper, int ype
     if ((!xper && (i <= 0 || i >= L.nx + 1)) || (!yper && (j <= 0 || j >= L.ny + 1))) msk[t] = 0.0;
 }
 
+// compare the analytic box coefficients with the arrays produced by the reference's setup
+// algorithm; any mismatch raises the flag and the generic path stays in use
+__global__ void __launch_bounds__(256)
+k_check_box(Level L, Box g, int has_coarse, int is_coarse, Box gc, int* __restrict__ flag)
+{
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)L.n) return;
+    int ai = (int)(t % L.sj);
+    long long q = t / L.sj;
+    int aj = (int)(q % (L.ny + 2 * NH)), ak = (int)(q / (L.ny + 2 * NH));
+    // only what the box kernels rely on is compared: idiag on the sweep-1 domain (interior + 1 ring),
+    // msk, diag, Rcoef, Pcoef on the interior (beyond ring 2 the halo of levels narrower than nh
+    // holds stale copies, mod_halo.f90:235-262 with overlapping sections)
+    int c = cnt_xy(g, ai, aj) + cnt_z(g, ak);
+    const bool ring1 = ai >= NH - 1 && ai <= L.nx + NH && aj >= NH - 1 && aj <= L.ny + NH && ak >= NH - 1 && ak <= L.nz - NH;
+    const bool interior = ai >= NH && ai < L.nx + NH && aj >= NH && aj < L.ny + NH && ak >= NH && ak < L.nz - NH;
+    bool bad = ring1 && L.idiag[t] != (c > 0 ? 1.0 / (double)c : 0.0);
+    if (interior && (L.msk[t] != 1.0 || L.diag[t] != (double)c)) bad = true;
+    if (interior && is_coarse && L.Rcoef[t] != 0.5) bad = true;
+    if (interior && has_coarse) {
+        int i = ai - NH + 1, j = aj - NH + 1, k = ak + 1;
+        int ic = (i + 1) / 2, jc = (j + 1) / 2;
+        int di = (i & 1) ? -1 : 1, dj = (j & 1) ? -1 : 1;
+        int upper = (k - (1 + NH)) & 1;
+        int kc = NH + (k - upper + 1 - NH) / 2;
+        int ko = upper ? kc + 1 : kc - 1;
+        int e = (int)in_x(gc, ic + di - 1 + NH) + (int)in_y(gc, jc + dj - 1 + NH) + (int)in_z(gc, ko - 1);
+        if (L.Pcoef[t] != pcoef_of(e)) bad = true;
+    }
+    if (bad) atomicOr(flag, 1);
+}
+
 // b_mg[idx] = div  /  p = x_mg[idx]*scale   (core/mgfordriver.py:72,78)
 __global__ void __launch_bounds__(256)
 k_embed(double* __restrict__ bmg, const double* __restrict__ div, Level L, int nz, int ny, int nx,
@@ -239,6 +373,202 @@ k_extract(const double* __restrict__ xmg, double* __restrict__ p, Level L, int n
         xmg[(long long)(k + k0) * L.sk + (long long)(j + j0) * L.sj + (i + i0)] * scale;
 }
 
+// =================================================================================================
+//  box kernels (analytic coefficients): the hot path
+// =================================================================================================
+
+// ---- fused smoother: both Jacobi sweeps of fsmoother3d in one pass over x and b ----------------
+// A CTA owns a (RJ-4) x 60 output tile of the padded plane and a chunk of planes; it streams
+// along k.  One warp per row, one double2 per lane: row loads are 512-byte coalesced vector loads.
+// Per owned column the thread keeps x[p-1..p+2], y[p-2..p], b[p-1..p+1] in registers; in-plane
+// neighbours go through two double-buffered shared-memory planes (one __syncthreads per plane).
+// Iteration p: stage 1 forms y[p] (sweep 1) on the tile + 1 ring from x[p-1], x[p], x[p+1];
+// stage 2 forms x'[p-1] (sweep 2) on the tile from y[p-2], y[p-1], y[p] and stores it.
+// Halo cells of the output buffer receive the old x, so the caller can swap x and y afterwards.
+constexpr int S2_RI = 64;
+constexpr int S2_TI = S2_RI - 4;
+
+template <int NW, int MR>
+__global__ void __launch_bounds__(NW * 32, (NW * MR <= 16) ? 2 : 1)
+k_smooth2(const double* __restrict__ x, const double* __restrict__ b, double* __restrict__ xo,
+          Box g, double omega, double cff1, int kchunk)
+{
+    constexpr int RJ = NW * MR;
+    __shared__ double2 sx[2][RJ][32];
+    __shared__ double2 sy[2][RJ][32];
+    __shared__ double s_recip[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < 8) s_recip[threadIdx.x] = threadIdx.x ? 1.0 / (double)threadIdx.x : 0.0;
+
+    const int ai = (int)blockIdx.x * S2_TI - 2 + 2 * lane;          // array column of element .x (even)
+    const int ajb = (int)blockIdx.y * (RJ - 4) - 2 + warp;          // row of chunk m: ajb + NW*m
+    const int ko0 = (int)blockIdx.z * kchunk;
+    const int ko1 = min(ko0 + kchunk, g.nz);
+    const int tx = g.nx + 2 * NH, ty = g.ny + 2 * NH;
+
+    long long off[MR];          // offset of the chunk inside a plane, -1 if outside the array
+    int cx0[MR], cx1[MR];       // in-plane neighbour counts of the two cells (or negative)
+    bool inter0[MR], inter1[MR], outp[MR];
+#pragma unroll
+    for (int m = 0; m < MR; m++) {
+        const int aj = ajb + NW * m, lj = warp + NW * m;
+        const bool inarr = ai >= 0 && ai < tx && aj >= 0 && aj < ty;
+        off[m] = inarr ? (long long)aj * g.sj + ai : -1;
+        cx0[m] = cnt_xy(g, ai, aj);
+        cx1[m] = cnt_xy(g, ai + 1, aj);
+        const bool jin = aj >= NH && aj < g.ny + NH;
+        inter0[m] = jin && ai >= NH && ai < g.nx + NH;
+        inter1[m] = jin && ai + 1 >= NH && ai + 1 < g.nx + NH;
+        outp[m] = inarr && lane >= 1 && lane <= 30 && lj >= 2 && lj < RJ - 2;
+    }
+    auto ld = [&](const double* __restrict__ a, int m, int p) -> double2 {
+        if (off[m] < 0 || p < 0 || p >= g.nz) return make_double2(0.0, 0.0);
+        return *reinterpret_cast<const double2*>(a + (long long)p * g.sk + off[m]);
+    };
+
+    double2 xm[MR], xc[MR], xp[MR], xn[MR], bm[MR], bc[MR], bn[MR], ym[MR], yc[MR];
+    const int p0 = ko0 - 1;
+#pragma unroll
+    for (int m = 0; m < MR; m++) {
+        xm[m] = ld(x, m, p0 - 1); xc[m] = ld(x, m, p0); xp[m] = ld(x, m, p0 + 1);
+        bm[m] = ld(b, m, p0 - 1); bc[m] = ld(b, m, p0);
+        ym[m] = make_double2(0.0, 0.0); yc[m] = make_double2(0.0, 0.0);
+    }
+    __syncthreads();
+
+    for (int p = p0; p <= ko1; p++) {
+        const int buf = p & 1, q = p - 1;
+#pragma unroll
+        for (int m = 0; m < MR; m++) {                    // prefetch one plane ahead
+            xn[m] = ld(x, m, p + 2);
+            bn[m] = ld(b, m, p + 1);
+            sx[buf][warp + NW * m][lane] = xc[m];
+        }
+        __syncthreads();                                  // x[p] (and y[p-1] from the last iteration) visible
+        const int cz1 = cnt_z(g, p), cz2 = cnt_z(g, q);
+        const bool qint = q >= NH && q < g.nz - NH;
+        double2 yp[MR];
+#pragma unroll
+        for (int m = 0; m < MR; m++) {
+            const int lj = warp + NW * m;
+            const int ju = lj > 0 ? lj - 1 : 0, jd = lj < RJ - 1 ? lj + 1 : RJ - 1;
+            const int ll = lane > 0 ? lane - 1 : 0, lr = lane < 31 ? lane + 1 : 31;
+            {   // ---- stage 1: sweep 1 at plane p
+                const double2 u = sx[buf][ju][lane], d = sx[buf][jd][lane];
+                const double l = sx[buf][lj][ll].y, r = sx[buf][lj][lr].x;
+                const double s0 = l + xc[m].y + u.x + d.x + xm[m].x + xp[m].x;
+                const double s1 = xc[m].x + r + u.y + d.y + xm[m].y + xp[m].y;
+                const double id0 = s_recip[max(cx0[m] + cz1, 0)], id1 = s_recip[max(cx1[m] + cz1, 0)];
+                yp[m].x = cff1 * xc[m].x + omega * (s0 - bc[m].x) * id0;
+                yp[m].y = cff1 * xc[m].y + omega * (s1 - bc[m].y) * id1;
+            }
+            {   // ---- stage 2: sweep 2 at plane q = p-1
+                const int yb = buf ^ 1;
+                const double2 u = sy[yb][ju][lane], d = sy[yb][jd][lane];
+                const double l = sy[yb][lj][ll].y, r = sy[yb][lj][lr].x;
+                const double s0 = l + yc[m].y + u.x + d.x + ym[m].x + yp[m].x;
+                const double s1 = yc[m].x + r + u.y + d.y + ym[m].y + yp[m].y;
+                const double id0 = s_recip[max(cx0[m] + cz2, 0)], id1 = s_recip[max(cx1[m] + cz2, 0)];
+                double2 o;
+                o.x = cff1 * yc[m].x + omega * (s0 - bm[m].x) * id0;
+                o.y = cff1 * yc[m].y + omega * (s1 - bm[m].y) * id1;
+                if (!(qint && inter0[m])) o.x = xm[m].x;          // outside the interior: keep x
+                if (!(qint && inter1[m])) o.y = xm[m].y;
+                if (outp[m] && q >= ko0 && q < ko1)
+                    *reinterpret_cast<double2*>(xo + (long long)q * g.sk + off[m]) = o;
+            }
+            sy[buf][lj][lane] = yp[m];
+        }
+#pragma unroll
+        for (int m = 0; m < MR; m++) {
+            xm[m] = xc[m]; xc[m] = xp[m]; xp[m] = xn[m];
+            bm[m] = bc[m]; bc[m] = bn[m];
+            ym[m] = yc[m]; yc[m] = yp[m];
+        }
+    }
+}
+
+// ---- residual on the interior with analytic diag; what happens to r depends on MODE ------------
+enum { RS_STORE, RS_NORM, RS_NORMB };
+// block (32,8): tile 32 x 8 of the interior, marching over a chunk of planes
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_resid(const double* __restrict__ x, const double* __restrict__ b, double* __restrict__ r,
+        Box g, int kchunk, double* __restrict__ partial)
+{
+    __shared__ double sh[8];
+    const int ai = NH + blockIdx.x * 32 + threadIdx.x;
+    const int aj = NH + blockIdx.y * 8 + threadIdx.y;
+    const int k0 = NH + blockIdx.z * kchunk, k1 = min(k0 + kchunk, g.nz - NH);
+    const bool act = ai < g.nx + NH && aj < g.ny + NH;
+    double acc = 0.0;
+    if (act) {
+        const int cxy = cnt_xy(g, ai, aj);
+        const long long o = (long long)aj * g.sj + ai;
+        if (MODE == RS_NORMB) {
+            for (int k = k0; k < k1; k++) { double v = b[(long long)k * g.sk + o]; acc = acc + v * v; }
+        } else {
+            double xm = x[(long long)(k0 - 1) * g.sk + o], xc = x[(long long)k0 * g.sk + o];
+            for (int k = k0; k < k1; k++) {
+                const long long c = (long long)k * g.sk + o;
+                const double xp = x[c + g.sk];
+                const double s = x[c - 1] + x[c + 1] + x[c - g.sj] + x[c + g.sj] + xm + xp;
+                const double diag = (double)(cxy + cnt_z(g, k));
+                const double rv = b[c] + diag * xc - s;
+                if (MODE == RS_STORE) r[c] = rv; else acc = acc + rv * rv;
+                xm = xc; xc = xp;
+            }
+        }
+    }
+    if (MODE != RS_STORE) {
+        const int tid = threadIdx.y * 32 + threadIdx.x;
+        for (int o = 16; o > 0; o >>= 1) acc = acc + __shfl_xor_sync(0xffffffffu, acc, o);
+        if ((tid & 31) == 0) sh[tid >> 5] = acc;
+        __syncthreads();
+        if (tid == 0) {
+            double t = 0.0;
+            for (int w = 0; w < 8; w++) t = t + sh[w];
+            partial[((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = t;
+        }
+    }
+}
+
+// ---- residual + restriction: b_c = 0.5 * sum_8 r_f, r never stored --------------------------------
+// one thread per coarse column, marching over coarse planes; block (32,8) coarse cells
+__global__ void __launch_bounds__(256)
+k_resid_restrict(const double* __restrict__ x, const double* __restrict__ b, double* __restrict__ bc,
+                 Box g, Box gc, int kchunk)
+{
+    const int ic = blockIdx.x * 32 + threadIdx.x, jc = blockIdx.y * 8 + threadIdx.y;    // 0-based interior coarse
+    if (ic >= gc.nx || jc >= gc.ny) return;
+    const int kc0 = blockIdx.z * kchunk, kc1 = min(kc0 + kchunk, gc.nz - 2 * NH);
+    const int ai = NH + 2 * ic, aj = NH + 2 * jc;
+    int cxy[2][2];
+#pragma unroll
+    for (int dj = 0; dj < 2; dj++)
+#pragma unroll
+        for (int di = 0; di < 2; di++) cxy[dj][di] = cnt_xy(g, ai + di, aj + dj);
+    const long long o = (long long)aj * g.sj + ai;
+    for (int kc = kc0; kc < kc1; kc++) {
+        const int k = NH + 2 * kc;
+        double s = 0.0;
+#pragma unroll
+        for (int dk = 0; dk < 2; dk++) {
+            const int cz = cnt_z(g, k + dk);
+#pragma unroll
+            for (int dj = 0; dj < 2; dj++)
+#pragma unroll
+                for (int di = 0; di < 2; di++) {
+                    const long long c = (long long)(k + dk) * g.sk + o + (long long)dj * g.sj + di;
+                    const double sum6 = x[c - 1] + x[c + 1] + x[c - g.sj] + x[c + g.sj] + x[c - g.sk] + x[c + g.sk];
+                    const double rv = b[c] + (double)(cxy[dj][di] + cz) * x[c] - sum6;
+                    s = (dk == 0 && dj == 0 && di == 0) ? rv : s + rv;
+                }
+        }
+        bc[(long long)(NH + kc) * gc.sk + (long long)(NH + jc) * gc.sj + (NH + ic)] = 0.5 * s;
+    }
+}
+
 inline int ew_blocks(long long n)
 {
     long long b = (n + 255) / 256;
@@ -246,6 +576,7 @@ inline int ew_blocks(long long n)
 }
 
 #define LAUNCH_OK(mg) NY_CHECK_LAUNCH((mg)->ctx)
+#define TRY(call) do { int _r = (call); if (_r != NY_OK) return _r; } while (0)
 
 template <int OP>
 int ew(ny_mg* mg, cudaStream_t st, double* dst, const double* a, const double* b, double val, size_t n)
@@ -275,10 +606,8 @@ int assign_box(ny_mg* mg, cudaStream_t st, const Level& L, double* a, int di0, i
     return NY_OK;
 }
 
-#define TRY(call) do { int _r = (call); if (_r != NY_OK) return _r; } while (0)
-
-// mod_halo.f90:235-262 exchange_with_myself, statement by statement
-int fill(ny_mg* mg, cudaStream_t st, const Level& L, double* a)
+// mod_halo.f90:235-262 exchange_with_myself, statement by statement (tiny levels)
+int fill_sequential(ny_mg* mg, cudaStream_t st, const Level& L, double* a, bool wrap_z)
 {
     const int nh = mg->nh, nx = L.nx, ny = L.ny, nz = L.nz;
     if (mg->xper) {
@@ -298,10 +627,38 @@ int fill(ny_mg* mg, cudaStream_t st, const Level& L, double* a)
         TRY(assign_box(mg, st, L, a, nx + 1, 1 - nh, 1, 1, ny - nh + 1, 1, nh, nh, nz, ov));
         TRY(assign_box(mg, st, L, a, 1 - nh, 1 - nh, 1, nx - nh + 1, ny - nh + 1, 1, nh, nh, nz, ov));
     }
-    if (mg->zper) {
+    if (wrap_z) {
         bool ov = (nz - 2 * nh) < nh;
         TRY(assign_box(mg, st, L, a, 1 - nh, 1 - nh, 1, 1 - nh, 1 - nh, nz - 2 * nh + 1, nx + 2 * nh, ny + 2 * nh, nh, ov));
         TRY(assign_box(mg, st, L, a, 1 - nh, 1 - nh, nz - nh + 1, 1 - nh, 1 - nh, nh + 1, nx + 2 * nh, ny + 2 * nh, nh, ov));
+    }
+    return NY_OK;
+}
+
+// halo fill of a level array: periodic wraps locally, z faces of distributed levels through NCCL
+int fill(ny_mg* mg, cudaStream_t st, const Level& L, double* a)
+{
+    const int nh = mg->nh;
+    const bool dist = !L.gathered;
+    const bool wrap_z = mg->zper && !dist;
+    if (mg->xper || mg->yper || wrap_z) {
+        const int nzi = L.nz - 2 * nh;
+        const bool simple = (!mg->xper || L.nx >= nh) && (!mg->yper || L.ny >= nh) && (!wrap_z || nzi >= nh);
+        if (simple) {
+            const long long n0 = 2LL * nh * L.sk;
+            const long long n1 = mg->yper ? (long long)nzi * 2 * nh * L.sj : 0;
+            const long long n2 = mg->xper ? (long long)nzi * L.ny * 2 * nh : 0;
+            const long long tot = n0 + n1 + n2;
+            k_fill_periodic<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(a, L.nx, L.ny, L.nz, L.sj, L.sk, mg->xper,
+                                                                            mg->yper, wrap_z ? 1 : 0, n0, n1, n2);
+            LAUNCH_OK(mg);
+        } else {
+            TRY(fill_sequential(mg, st, L, a, wrap_z));
+        }
+    }
+    if (dist && (mg->below >= 0 || mg->above >= 0)) {
+        double* arr[1] = {a};
+        TRY(ny_comm_exchange_z(mg->comm, arr, 1, (size_t)L.sk, nh, L.nz - 2 * nh, nh, mg->below, mg->above, st));
     }
     return NY_OK;
 }
@@ -311,63 +668,197 @@ inline dim3 box_grid(int ni, int nj, int nk, dim3 b)
     return dim3((ni + b.x - 1) / b.x, (nj + b.y - 1) / b.y, (nk + b.z - 1) / b.z);
 }
 
+inline int chunk_for(ny_mg* mg, int planes, long long tiles, int min_chunk)
+{   // split the planes so that the launch has a few CTAs per SM, but never below min_chunk planes
+    long long target = (long long)mg->ctx->num_sms * 32;
+    long long nchunks = (target + tiles - 1) / tiles;
+    if (nchunks < 1) nchunks = 1;
+    int chunk = (int)((planes + nchunks - 1) / nchunks);
+    if (chunk < min_chunk) chunk = min_chunk;
+    if (chunk > planes) chunk = planes > 0 ? planes : 1;
+    return chunk;
+}
+
 int smooth(ny_mg* mg, cudaStream_t st, int lev)
 {
     Level& L = mg->lev[lev - 1];
     const int nh = mg->nh;
     const double omega = mg->omega, cff1 = 1.0 - omega;
-    ny_prof_scope ps(mg->ctx, lev == 1 ? NY_PROF_MG_SMOOTH_FINE : NY_PROF_MG_COARSE, st);
-    dim3 b(32, 4, 2);
-    k_sweep<<<box_grid(L.nx + 2, L.ny + 2, L.nz - 2 * nh + 2, b), b, 0, st>>>(
-        L.x, L.y, L.b, L.idiag, omega, cff1, L, nh, 0, L.nx + 1, 0, L.ny + 1, nh, L.nz + 1 - nh);
-    LAUNCH_OK(mg);
-    k_sweep<<<box_grid(L.nx, L.ny, L.nz - 2 * nh, b), b, 0, st>>>(
-        L.y, L.x, L.b, L.idiag, omega, cff1, L, nh, 1, L.nx, 1, L.ny, nh + 1, L.nz - nh);
-    LAUNCH_OK(mg);
+    {
+        ny_prof_scope ps(mg->ctx, lev == 1 ? NY_PROF_MG_SMOOTH_FINE : NY_PROF_MG_COARSE, st);
+        if (mg->box) {
+            constexpr int NW = 8, MR = 2, RJ = NW * MR;
+            const int gx = (L.nx + 2 * nh + S2_TI - 1) / S2_TI, gy = (L.ny + 2 * nh + (RJ - 4) - 1) / (RJ - 4);
+            const int chunk = chunk_for(mg, L.nz, (long long)gx * gy, 16);
+            dim3 grid(gx, gy, (L.nz + chunk - 1) / chunk);
+            k_smooth2<NW, MR><<<grid, NW * 32, 0, st>>>(L.x, L.b, L.y, box_of(mg, L), omega, cff1, chunk);
+            LAUNCH_OK(mg);
+            double* t = L.x; L.x = L.y; L.y = t;
+        } else {
+            dim3 b(32, 4, 2);
+            k_sweep<<<box_grid(L.nx + 2, L.ny + 2, L.nz - 2 * nh + 2, b), b, 0, st>>>(
+                L.x, L.y, L.b, L.idiag, omega, cff1, L, nh, 0, L.nx + 1, 0, L.ny + 1, nh, L.nz + 1 - nh);
+            LAUNCH_OK(mg);
+            k_sweep<<<box_grid(L.nx, L.ny, L.nz - 2 * nh, b), b, 0, st>>>(
+                L.y, L.x, L.b, L.idiag, omega, cff1, L, nh, 1, L.nx, 1, L.ny, nh + 1, L.nz - nh);
+            LAUNCH_OK(mg);
+        }
+    }
     return fill(mg, st, L, L.x);
+}
+
+// launch geometry of the interior-marching kernels (block 32 x 8)
+struct March { dim3 grid; int chunk; int nparts; };
+inline March march_geom(ny_mg* mg, int nx, int ny, int nzi)
+{
+    March m;
+    const int gx = (nx + 31) / 32, gy = (ny + 7) / 8;
+    m.chunk = chunk_for(mg, nzi, (long long)gx * gy, 8);
+    int gz = (nzi + m.chunk - 1) / m.chunk;
+    while ((long long)gx * gy * gz > MAX_PARTIALS) { m.chunk *= 2; gz = (nzi + m.chunk - 1) / m.chunk; }
+    m.grid = dim3(gx, gy, gz);
+    m.nparts = gx * gy * gz;
+    return m;
 }
 
 int residual(ny_mg* mg, cudaStream_t st, int lev)
 {
     Level& L = mg->lev[lev - 1];
-    ny_prof_scope ps(mg->ctx, lev == 1 ? NY_PROF_MG_RESIDUAL_FINE : NY_PROF_MG_COARSE, st);
-    dim3 b(32, 4, 2);
-    k_residual<<<box_grid(L.nx, L.ny, L.nz - 2 * mg->nh, b), b, 0, st>>>(L.x, L.b, L.r, L.msk, L.diag, L, mg->nh);
-    LAUNCH_OK(mg);
+    {
+        ny_prof_scope ps(mg->ctx, lev == 1 ? NY_PROF_MG_RESIDUAL_FINE : NY_PROF_MG_COARSE, st);
+        if (mg->box) {
+            March m = march_geom(mg, L.nx, L.ny, L.nz - 2 * mg->nh);
+            k_resid<RS_STORE><<<m.grid, dim3(32, 8), 0, st>>>(L.x, L.b, L.r, box_of(mg, L), m.chunk, nullptr);
+        } else {
+            dim3 b(32, 4, 2);
+            k_residual<<<box_grid(L.nx, L.ny, L.nz - 2 * mg->nh, b), b, 0, st>>>(L.x, L.b, L.r, L.msk, L.diag, L, mg->nh);
+        }
+        LAUNCH_OK(mg);
+    }
     return fill(mg, st, L, L.r);
+}
+
+// the coarse level as seen from the slab of the finer level: the level itself, or the window of a
+// gathered level that lies under this rank's slab
+Level coarse_view(ny_mg* mg, int lev)
+{
+    const Level& F = mg->lev[lev - 1];
+    Level C = mg->lev[lev];
+    if (!F.gathered && C.gathered) {
+        const int nzc = (F.nz - 2 * mg->nh) / 2;                       // coarse planes under this slab
+        const size_t off = (size_t)mg->rank * nzc * C.sk;
+        C.nz = nzc + 2 * mg->nh;
+        C.n = (size_t)C.sk * C.nz;
+        C.zlo = F.zlo; C.zhi = F.zhi;
+        C.x += off; C.b += off; C.r += off; C.y += off;
+    }
+    return C;
+}
+
+// after the restriction wrote this rank's part of a gathered level: collect the other parts
+int gather_after_restriction(ny_mg* mg, cudaStream_t st, int lev)
+{
+    const Level& F = mg->lev[lev - 1];
+    Level& C = mg->lev[lev];
+    if (F.gathered || !C.gathered) return NY_OK;
+    const size_t cnt = (size_t)((F.nz - 2 * mg->nh) / 2) * C.sk;
+    return ny_comm_allgather_inplace(mg->comm, C.b + (size_t)mg->nh * C.sk, cnt, st);
 }
 
 int restriction(ny_mg* mg, cudaStream_t st, int lev, bool from_b)
 {
-    Level &F = mg->lev[lev - 1], &C = mg->lev[lev];
-    ny_prof_scope ps(mg->ctx, lev == 1 ? NY_PROF_MG_RESTRICT_FINE : NY_PROF_MG_COARSE, st);
-    dim3 b(32, 4, 2);
-    k_restrict<<<box_grid(C.nx, C.ny, C.nz - 2 * mg->nh, b), b, 0, st>>>(from_b ? F.b : F.r, C.b, C.Rcoef, F, C, mg->nh);
-    LAUNCH_OK(mg);
-    NY_CUDA(cudaMemsetAsync(C.x, 0, C.n * sizeof(double), st));           // operators.f90:209
+    Level& F = mg->lev[lev - 1];
+    Level& C = mg->lev[lev];
+    Level V = coarse_view(mg, lev);
+    {
+        ny_prof_scope ps(mg->ctx, lev == 1 ? NY_PROF_MG_RESTRICT_FINE : NY_PROF_MG_COARSE, st);
+        dim3 b(32, 4, 2);
+        k_restrict<<<box_grid(V.nx, V.ny, V.nz - 2 * mg->nh, b), b, 0, st>>>(
+            from_b ? F.b : F.r, V.b, mg->box ? nullptr : C.Rcoef, F, V, mg->nh);
+        LAUNCH_OK(mg);
+        NY_CUDA(cudaMemsetAsync(C.x, 0, C.n * sizeof(double), st));           // operators.f90:209
+    }
+    TRY(gather_after_restriction(mg, st, lev));
+    return fill(mg, st, C, C.b);
+}
+
+// box path of "residual(lev); restriction(lev)" without storing r
+int residual_restriction(ny_mg* mg, cudaStream_t st, int lev)
+{
+    if (!mg->box) { TRY(residual(mg, st, lev)); return restriction(mg, st, lev, false); }
+    Level& F = mg->lev[lev - 1];
+    Level& C = mg->lev[lev];
+    Level V = coarse_view(mg, lev);
+    {
+        ny_prof_scope ps(mg->ctx, lev == 1 ? NY_PROF_MG_RESIDUAL_FINE : NY_PROF_MG_COARSE, st);
+        March m = march_geom(mg, V.nx, V.ny, V.nz - 2 * mg->nh);
+        k_resid_restrict<<<m.grid, dim3(32, 8), 0, st>>>(F.x, F.b, V.b, box_of(mg, F), box_of(mg, V), m.chunk);
+        LAUNCH_OK(mg);
+        NY_CUDA(cudaMemsetAsync(C.x, 0, C.n * sizeof(double), st));
+    }
+    TRY(gather_after_restriction(mg, st, lev));
     return fill(mg, st, C, C.b);
 }
 
 int prolongation(ny_mg* mg, cudaStream_t st, int lev)
 {
-    Level &F = mg->lev[lev - 1], &C = mg->lev[lev];
-    ny_prof_scope ps(mg->ctx, lev == 1 ? NY_PROF_MG_PROLONG_FINE : NY_PROF_MG_COARSE, st);
-    dim3 b(32, 4, 2);
-    k_prolong<<<box_grid(F.nx, F.ny, F.nz - 2 * mg->nh, b), b, 0, st>>>(F.x, C.x, F.Pcoef, F, C, mg->nh);
-    LAUNCH_OK(mg);
+    Level& F = mg->lev[lev - 1];
+    Level V = coarse_view(mg, lev);
+    {
+        ny_prof_scope ps(mg->ctx, lev == 1 ? NY_PROF_MG_PROLONG_FINE : NY_PROF_MG_COARSE, st);
+        dim3 b(32, 4, 2);
+        k_prolong<<<box_grid(F.nx, F.ny, F.nz - 2 * mg->nh, b), b, 0, st>>>(
+            F.x, V.x, mg->box ? nullptr : F.Pcoef, F, V, box_of(mg, V), mg->nh);
+        LAUNCH_OK(mg);
+    }
     return fill(mg, st, F, F.x);
 }
 
-// enqueue sum(msk*v^2) of level 1 into d_red[slot]
-int norm_async(ny_mg* mg, cudaStream_t st, const double* v, int slot)
+// enqueue the global sum of the per-block partials into d_red[MAX_PARTIALS + slot]
+int finish_sum(ny_mg* mg, cudaStream_t st, int nparts, int slot)
+{
+    k_sum_final<<<1, 256, 0, st>>>(mg->d_red, nparts, mg->d_red + MAX_PARTIALS + slot);
+    LAUNCH_OK(mg);
+    return ny_comm_allreduce(mg->comm, mg->d_red + MAX_PARTIALS + slot, 1, 0, st);
+}
+
+// sum(msk*b^2) of level 1 -> slot 0
+int norm_b_async(ny_mg* mg, cudaStream_t st)
 {
     Level& L = mg->lev[0];
     ny_prof_scope ps(mg->ctx, NY_PROF_MG_NORM, st);
-    k_norm_partial<<<NORM_BLOCKS, 256, 0, st>>>(L.msk, v, L, mg->nh, mg->d_red + 2);
+    int nparts;
+    if (mg->box) {
+        March m = march_geom(mg, L.nx, L.ny, L.nz - 2 * mg->nh);
+        k_resid<RS_NORMB><<<m.grid, dim3(32, 8), 0, st>>>(nullptr, L.b, nullptr, box_of(mg, L), m.chunk, mg->d_red);
+        nparts = m.nparts;
+    } else {
+        nparts = 1184;
+        k_norm_partial<<<nparts, 256, 0, st>>>(L.msk, L.b, L, mg->nh, mg->d_red);
+    }
     LAUNCH_OK(mg);
-    k_norm_final<<<1, 256, 0, st>>>(mg->d_red + 2, NORM_BLOCKS, mg->d_red + slot);
+    return finish_sum(mg, st, nparts, 0);
+}
+
+// residual(1) followed by sum(msk*r^2) -> slot 1
+int norm_r_async(ny_mg* mg, cudaStream_t st)
+{
+    Level& L = mg->lev[0];
+    int nparts;
+    if (mg->box) {
+        ny_prof_scope ps(mg->ctx, NY_PROF_MG_NORM, st);
+        March m = march_geom(mg, L.nx, L.ny, L.nz - 2 * mg->nh);
+        k_resid<RS_NORM><<<m.grid, dim3(32, 8), 0, st>>>(L.x, L.b, nullptr, box_of(mg, L), m.chunk, mg->d_red);
+        LAUNCH_OK(mg);
+        nparts = m.nparts;
+        return finish_sum(mg, st, nparts, 1);
+    }
+    TRY(residual(mg, st, 1));
+    ny_prof_scope ps(mg->ctx, NY_PROF_MG_NORM, st);
+    nparts = 1184;
+    k_norm_partial<<<nparts, 256, 0, st>>>(L.msk, L.r, L, mg->nh, mg->d_red);
     LAUNCH_OK(mg);
-    return NY_OK;
+    return finish_sum(mg, st, nparts, 1);
 }
 
 int vcycle(ny_mg* mg, cudaStream_t st)
@@ -375,8 +866,7 @@ int vcycle(ny_mg* mg, cudaStream_t st)
     const int lev1 = mg->nlevels - 1;
     for (int lev = 1; lev <= lev1; lev++) {
         TRY(smooth(mg, st, lev));
-        TRY(residual(mg, st, lev));
-        TRY(restriction(mg, st, lev, false));
+        TRY(residual_restriction(mg, st, lev));
     }
     TRY(smooth(mg, st, lev1 + 1));
     for (int lev = lev1; lev >= 1; lev--) {
@@ -386,11 +876,11 @@ int vcycle(ny_mg* mg, cudaStream_t st)
     return NY_OK;
 }
 
+// operators.f90:461-505 on one rank, through the generic kernels
 int setup_operators(ny_mg* mg, cudaStream_t st)
 {
     const int nl = mg->nlevels;
-    // setup_fine_msk (mg_setup.f90:213-223): halo-fill the finest mask
-    TRY(fill(mg, st, mg->lev[0], mg->lev[0].msk));
+    TRY(fill(mg, st, mg->lev[0], mg->lev[0].msk));               // setup_fine_msk, mg_setup.f90:213-223
     for (int lev = 1; lev <= nl - 1; lev++) {                    // compute_msk, operators.f90:299-335
         Level &F = mg->lev[lev - 1], &C = mg->lev[lev];
         TRY(ew<EW_SET>(mg, st, C.msk, nullptr, nullptr, 1.0, C.n));
@@ -432,6 +922,24 @@ int setup_operators(ny_mg* mg, cudaStream_t st)
     return NY_OK;
 }
 
+// decide whether the analytic box coefficients reproduce the arrays exactly
+int verify_box(ny_mg* mg, cudaStream_t st)
+{
+    NY_CUDA(cudaMemsetAsync(mg->d_flag, 0, sizeof(int), st));
+    for (int l = 0; l < mg->nlevels; l++) {
+        Level& L = mg->lev[l];
+        const bool has_c = l + 1 < mg->nlevels;
+        Box gc = box_of(mg, mg->lev[has_c ? l + 1 : l]);
+        k_check_box<<<(unsigned)((L.n + 255) / 256), 256, 0, st>>>(L, box_of(mg, L), has_c ? 1 : 0, l > 0 ? 1 : 0, gc, mg->d_flag);
+        LAUNCH_OK(mg);
+    }
+    int flag = 1;
+    NY_CUDA(cudaMemcpyAsync(&flag, mg->d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    NY_CUDA(cudaStreamSynchronize(st));
+    mg->box = flag == 0;
+    return NY_OK;
+}
+
 double* var_ptr(ny_mg* mg, int lev, int ivar)
 {
     Level& L = mg->lev[lev - 1];
@@ -440,6 +948,115 @@ double* var_ptr(ny_mg* mg, int lev, int ivar)
     case NY_MG_DIAG: return L.diag; case NY_MG_IDIAG: return L.idiag; case NY_MG_MSK: return L.msk;
     case NY_MG_RCOEF: return L.Rcoef; case NY_MG_PCOEF: return L.Pcoef; default: return nullptr;
     }
+}
+
+int create(ny_ctx* ctx, ny_comm* comm, int nx, int ny, int nz_global, int topology, ny_mg** out)
+{
+    NY_REQUIRE(ctx && out, "null argument");
+    NY_REQUIRE(nx >= 2 && ny >= 2 && nz_global >= 1, "grid too small");
+    NY_REQUIRE(topology >= NY_TOPO_CLOSED && topology <= NY_TOPO_XYZPERIO, "unknown topology");
+    const int P = comm ? comm->nranks : 1, rank = comm ? comm->rank : 0;
+    NY_REQUIRE(nz_global % P == 0, "global nz must be a multiple of the number of slabs");
+    ny_mg* mg = new ny_mg();
+    memset(mg, 0, sizeof(ny_mg));
+    mg->ctx = ctx; mg->comm = P > 1 ? comm : nullptr; mg->nranks = P; mg->rank = rank;
+    mg->nh = NH; mg->maxite = 20; mg->tol = 1e-6; mg->omega = 0.9;          // mg_types.f90:15-26
+    mg->topology = topology;
+    mg->xper = topology == NY_TOPO_XPERIO || topology == NY_TOPO_XYPERIO || topology == NY_TOPO_XYZPERIO;
+    mg->yper = topology == NY_TOPO_YPERIO || topology == NY_TOPO_XYPERIO || topology == NY_TOPO_XYZPERIO;
+    mg->zper = topology == NY_TOPO_ZPERIO || topology == NY_TOPO_XYZPERIO;
+    mg->below = rank > 0 ? rank - 1 : (mg->zper && P > 1 ? P - 1 : -1);
+    mg->above = rank < P - 1 ? rank + 1 : (mg->zper && P > 1 ? 0 : -1);
+    const int nh = mg->nh;
+    // create_hierarchy, mg_setup.f90:225-307, on the GLOBAL grid.  The Fortran loops for ever (and
+    // overruns its level table) when neither nx nor ny passes through 2; refuse instead.
+    int gx[MAXLEV], gy[MAXLEV], gz[MAXLEV];
+    int x = nx, y = ny, z = nz_global, i = 0;
+    gx[0] = x; gy[0] = y; gz[0] = z;
+    while (!(x == 2 || y == 2)) {
+        if ((x & 1) || (y & 1) || x < 2 || y < 2 || (z & 1) || z < 2 || i + 1 >= MAXLEV) {
+            ny_set_error("ny_mg_create: %dx%dx%d cannot be halved down to nx==2 or ny==2 with even extents "
+                         "(core/mgfor/mg_setup.f90:262-303)", nx, ny, nz_global);
+            delete mg;
+            return NY_ERR_GRID;
+        }
+        x /= 2; y /= 2; z /= 2;
+        i++;
+        gx[i] = x; gy[i] = y; gz[i] = z;
+    }
+    mg->nlevels = i + 1;
+    // slabs: a level stays distributed while its slab is at least 4 planes thick and the level has
+    // more than 64^3 cells; from the first level that is not, everything is gathered
+    mg->glev = 0;
+    if (P > 1) {
+        int l = 0;
+        while (l < mg->nlevels && gz[l] % P == 0 && gz[l] / P >= 4 && (long long)gx[l] * gy[l] * gz[l] > 262144LL) l++;
+        mg->glev = l;
+        if (l == 0) {
+            ny_set_error("ny_mg_create: the finest level (%dx%dx%d on %d slabs) is too small to be distributed",
+                         nx, ny, nz_global, P);
+            delete mg;
+            return NY_ERR_GRID;
+        }
+    }
+    size_t tmp_need = 1;
+    for (int l = 0; l < mg->nlevels; l++) {
+        Level& L = mg->lev[l];
+        L.gathered = l >= mg->glev;
+        L.nx = gx[l]; L.ny = gy[l];
+        L.nz = (L.gathered ? gz[l] : gz[l] / P) + 2 * nh;
+        L.zlo = L.gathered ? mg->zper : (rank > 0 || mg->zper);
+        L.zhi = L.gathered ? mg->zper : (rank < P - 1 || mg->zper);
+        L.sj = L.nx + 2 * nh;
+        L.sk = L.sj * (L.ny + 2 * nh);
+        L.n = (size_t)L.sk * (size_t)L.nz;
+        double** all[] = {&L.x, &L.b, &L.r, &L.y, &L.diag, &L.idiag, &L.Rcoef, &L.Pcoef, &L.msk};
+        const int nalloc = P > 1 ? 4 : 9;                       // slabs use the analytic coefficients only
+        for (int a = 0; a < nalloc; a++) {
+            cudaError_t e = cudaMalloc(all[a], L.n * sizeof(double));
+            if (e != cudaSuccess) {
+                ny_set_error("ny_mg_create: cudaMalloc of level %d failed: %s", l + 1, cudaGetErrorString(e));
+                ny_mg_destroy(mg);
+                return NY_ERR_CUDA;
+            }
+            cudaMemset(*all[a], 0, L.n * sizeof(double));       // Fortran leaves these uninitialised
+        }
+        // staging is only needed where a periodic section can overlap itself (tiny levels)
+        if (L.nx < nh || L.ny < nh || (L.nz - 2 * nh) < nh) {
+            size_t need = (size_t)L.sk * nh;
+            size_t need2 = (size_t)nh * (L.ny + 2 * nh) * L.nz;
+            size_t need3 = (size_t)nh * (L.nx + 2 * nh) * L.nz;
+            if (need > tmp_need) tmp_need = need;
+            if (need2 > tmp_need) tmp_need = need2;
+            if (need3 > tmp_need) tmp_need = need3;
+        }
+    }
+    mg->tmp_doubles = tmp_need;
+    if (cudaMalloc(&mg->tmp, tmp_need * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&mg->d_red, (MAX_PARTIALS + 4) * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&mg->d_flag, sizeof(int)) != cudaSuccess) {
+        ny_set_error("ny_mg_create: cudaMalloc failed");
+        ny_mg_destroy(mg);
+        return NY_ERR_CUDA;
+    }
+    cudaStream_t st = 0;
+    int r = NY_OK;
+    if (P == 1) {
+        for (int l = 0; l < mg->nlevels; l++) {
+            Level& L = mg->lev[l];
+            k_default_msk<<<(unsigned)((L.n + 255) / 256), 256, 0, st>>>(L.msk, L, nh, mg->zper);
+            ctx->launches++;
+        }
+        mg->box = 0;                                            // the setup itself runs on the generic kernels
+        r = setup_operators(mg, st);
+        if (r == NY_OK) r = verify_box(mg, st);
+    } else {
+        mg->box = 1;
+    }
+    if (r == NY_OK && cudaStreamSynchronize(st) != cudaSuccess) { ny_set_error("ny_mg_create: setup failed"); r = NY_ERR_CUDA; }
+    if (r != NY_OK) { ny_mg_destroy(mg); return r; }
+    *out = mg;
+    return NY_OK;
 }
 
 }  // namespace
@@ -454,86 +1071,32 @@ extern "C" void ny_mg_destroy(ny_mg* mg)
     }
     if (mg->tmp) cudaFree(mg->tmp);
     if (mg->d_red) cudaFree(mg->d_red);
+    if (mg->d_flag) cudaFree(mg->d_flag);
     delete mg;
 }
 
 extern "C" int ny_mg_create(ny_ctx* ctx, int nx, int ny, int nz, int topology, ny_mg** out)
 {
-    NY_REQUIRE(ctx && out, "null argument");
-    NY_REQUIRE(nx >= 2 && ny >= 2 && nz >= 1, "grid too small");
-    NY_REQUIRE(topology >= NY_TOPO_CLOSED && topology <= NY_TOPO_XYZPERIO, "unknown topology");
-    ny_mg* mg = new ny_mg();
-    memset(mg, 0, sizeof(ny_mg));
-    mg->ctx = ctx;
-    mg->nh = 3; mg->maxite = 20; mg->tol = 1e-6; mg->omega = 0.9;          // mg_types.f90:15-26
-    mg->topology = topology;
-    mg->xper = topology == NY_TOPO_XPERIO || topology == NY_TOPO_XYPERIO || topology == NY_TOPO_XYZPERIO;
-    mg->yper = topology == NY_TOPO_YPERIO || topology == NY_TOPO_XYPERIO || topology == NY_TOPO_XYZPERIO;
-    mg->zper = topology == NY_TOPO_ZPERIO || topology == NY_TOPO_XYZPERIO;
-    const int nh = mg->nh;
-    // create_hierarchy, mg_setup.f90:225-307 (one process: never glued).  The Fortran loops for
-    // ever (and overruns its level table) when neither nx nor ny passes through 2; refuse instead.
-    int x = nx, y = ny, z = nz + 2 * nh, i = 0;
-    mg->lev[0].nx = x; mg->lev[0].ny = y; mg->lev[0].nz = z;
-    while (!(x == 2 || y == 2)) {
-        if ((x & 1) || (y & 1) || x < 2 || y < 2 || ((z - 2 * nh) & 1) || (z - 2 * nh) < 2 || i + 1 >= MAXLEV) {
-            ny_set_error("ny_mg_create: %dx%dx%d cannot be halved down to nx==2 or ny==2 with even extents "
-                         "(core/mgfor/mg_setup.f90:262-303)", nx, ny, nz);
-            delete mg;
-            return NY_ERR_GRID;
-        }
-        x /= 2; y /= 2; z = z / 2 + nh;
-        i++;
-        mg->lev[i].nx = x; mg->lev[i].ny = y; mg->lev[i].nz = z;
-    }
-    mg->nlevels = i + 1;
-    size_t tmp_need = 1;
-    for (int l = 0; l < mg->nlevels; l++) {
-        Level& L = mg->lev[l];
-        L.sj = L.nx + 2 * nh;
-        L.sk = L.sj * (L.ny + 2 * nh);
-        L.n = (size_t)L.sk * (size_t)L.nz;
-        double** ptrs[] = {&L.x, &L.b, &L.r, &L.y, &L.diag, &L.idiag, &L.Rcoef, &L.Pcoef, &L.msk};
-        for (double** p : ptrs) {
-            cudaError_t e = cudaMalloc(p, L.n * sizeof(double));
-            if (e != cudaSuccess) {
-                ny_set_error("ny_mg_create: cudaMalloc of level %d failed: %s", l + 1, cudaGetErrorString(e));
-                ny_mg_destroy(mg);
-                return NY_ERR_CUDA;
-            }
-            cudaMemset(*p, 0, L.n * sizeof(double));             // Fortran leaves these uninitialised
-        }
-        // staging is only needed where a periodic section can overlap itself (tiny levels)
-        if (L.nx < nh || L.ny < nh || (L.nz - 2 * nh) < nh) {
-            size_t need = (size_t)L.sk * nh;
-            size_t need2 = (size_t)nh * (L.ny + 2 * nh) * L.nz;
-            size_t need3 = (size_t)nh * (L.nx + 2 * nh) * L.nz;
-            if (need > tmp_need) tmp_need = need;
-            if (need2 > tmp_need) tmp_need = need2;
-            if (need3 > tmp_need) tmp_need = need3;
-        }
-    }
-    mg->tmp_doubles = tmp_need;
-    if (cudaMalloc(&mg->tmp, tmp_need * sizeof(double)) != cudaSuccess ||
-        cudaMalloc(&mg->d_red, (NORM_BLOCKS + 2) * sizeof(double)) != cudaSuccess) {
-        ny_set_error("ny_mg_create: cudaMalloc failed");
-        ny_mg_destroy(mg);
-        return NY_ERR_CUDA;
-    }
-    cudaStream_t st = 0;
-    for (int l = 0; l < mg->nlevels; l++) {
-        Level& L = mg->lev[l];
-        k_default_msk<<<(unsigned)((L.n + 255) / 256), 256, 0, st>>>(L.msk, L, nh, mg->zper);
-        ctx->launches++;
-    }
-    int r = setup_operators(mg, st);
-    if (r == NY_OK && cudaStreamSynchronize(st) != cudaSuccess) { ny_set_error("ny_mg_create: setup failed"); r = NY_ERR_CUDA; }
-    if (r != NY_OK) { ny_mg_destroy(mg); return r; }
-    *out = mg;
-    return NY_OK;
+    return create(ctx, nullptr, nx, ny, nz, topology, out);
+}
+
+extern "C" int ny_mg_create_slab(ny_ctx* ctx, ny_comm* comm, int nx, int ny, int nz_global, int topology, ny_mg** out)
+{
+    return create(ctx, comm, nx, ny, nz_global, topology, out);
 }
 
 extern "C" int ny_mg_nlevels(ny_mg* mg) { return mg ? mg->nlevels : 0; }
+extern "C" int ny_mg_is_box(ny_mg* mg) { return mg ? mg->box : 0; }
+extern "C" int ny_mg_first_gathered_level(ny_mg* mg) { return mg ? mg->glev + 1 : 0; }
+
+extern "C" int ny_mg_set_fast_path(ny_mg* mg, int on)
+{
+    NY_REQUIRE(mg, "null argument");
+    NY_REQUIRE(mg->nranks == 1, "slab multigrids always run the box kernels (they hold no coefficient arrays)");
+    if (on) return verify_box(mg, 0);
+    mg->box = 0;
+    return NY_OK;
+}
 
 extern "C" int ny_mg_shape(ny_mg* mg, int lev, int shape[3])
 {
@@ -554,8 +1117,10 @@ extern "C" int ny_mg_set_array(ny_mg* mg, int lev, int ivar, const double* src, 
 {
     NY_REQUIRE(mg && src && lev >= 1 && lev <= mg->nlevels, "bad argument");
     NY_REQUIRE((ivar >= NY_MG_X && ivar <= NY_MG_Y) || ivar == NY_MG_MSK, "only x,b,r,y,msk can be set (pytools.f90:45-62)");
+    NY_REQUIRE(var_ptr(mg, lev, ivar), "this multigrid holds no such array (slab multigrids keep x, b, r, y only)");
     NY_CUDA(cudaMemcpyAsync(var_ptr(mg, lev, ivar), src, mg->lev[lev - 1].n * sizeof(double),
                             cudaMemcpyDeviceToDevice, ny_stream(stream)));
+    if (ivar == NY_MG_MSK) mg->box = 0;          // a user mask: coefficients are no longer those of a box
     return NY_OK;
 }
 
@@ -569,7 +1134,7 @@ extern "C" int ny_mg_get_array(ny_mg* mg, int lev, int ivar, double* dst, void* 
 
 static int read_scalars(ny_mg* mg, cudaStream_t st, int n)
 {
-    NY_CUDA(cudaMemcpyAsync(mg->ctx->h_pinned, mg->d_red, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    NY_CUDA(cudaMemcpyAsync(mg->ctx->h_pinned, mg->d_red + MAX_PARTIALS, n * sizeof(double), cudaMemcpyDeviceToHost, st));
     NY_CUDA(cudaStreamSynchronize(st));
     return NY_OK;
 }
@@ -579,31 +1144,24 @@ extern "C" int ny_mg_solve(ny_mg* mg, ny_mg_stats* stats, void* stream)
 {
     NY_REQUIRE(mg, "null argument");
     cudaStream_t st = ny_stream(stream);
-    Level& L = mg->lev[0];
     int nite = 0, nres = 0;
     double hist[32];
     // normb = sum(msk b^2); res = sum(msk r^2)/normb after residual(1)   (operators.f90:81-125)
-    TRY(norm_async(mg, st, L.b, 0));
-    TRY(read_scalars(mg, st, 1));
+    // both are enqueued before the first host read: one synchronisation instead of two
+    TRY(norm_b_async(mg, st));
+    TRY(norm_r_async(mg, st));
+    TRY(read_scalars(mg, st, 2));
     const double normb = mg->ctx->h_pinned[0];
-    double res = 0.0;
-    auto normresidual = [&]() -> int {
-        if (normb > 0.0) {
-            TRY(residual(mg, st, 1));
-            TRY(norm_async(mg, st, L.r, 1));
-            TRY(read_scalars(mg, st, 2));
-            res = mg->ctx->h_pinned[1] / normb;
-        } else res = 0.0;
-        return NY_OK;
-    };
-    TRY(normresidual());
+    double res = normb > 0.0 ? mg->ctx->h_pinned[1] / normb : 0.0;
     hist[nres++] = res;
     for (;;) {
         if (res < mg->tol) break;
         TRY(vcycle(mg, st));
         nite++;
         if (nite >= mg->maxite) break;
-        TRY(normresidual());
+        TRY(norm_r_async(mg, st));
+        TRY(read_scalars(mg, st, 2));
+        res = mg->ctx->h_pinned[1] / normb;
         if (nres < 32) hist[nres++] = res;
     }
     if (stats) {
@@ -630,7 +1188,7 @@ extern "C" int ny_mg_solve_directly(ny_mg* mg, double* p, const double* div, ny_
     }
     TRY(ny_mg_solve(mg, stats, stream));
     ny_prof_scope ps(mg->ctx, NY_PROF_MG_EMBED, st);
-    k_extract<<<g.grid, g.block, 0, st>>>(L.x, p, L, e.nz, e.ny, e.nx, lo[0], lo[1], lo[2], scale);
+    k_extract<<<g.grid, g.block, 0, st>>>(mg->lev[0].x, p, L, e.nz, e.ny, e.nx, lo[0], lo[1], lo[2], scale);
     LAUNCH_OK(mg);
     return NY_OK;
 }

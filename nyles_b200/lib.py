@@ -64,6 +64,17 @@ _PROTOS = {
     "ny_ts_rk3_stage3": ([_P, _P, _P, _P, _P, _D, _LL, _P], _I),
     "ny_max_speed2": ([_P, _P, _P, _P, _LL, C.POINTER(_D), _P], _I),
     "ny_halo_fill_self": ([_P, _P, ny_ext, _I, C.POINTER(_I * 3), _P], _I),
+    "ny_comm_unique_id": ([C.c_char_p], _I),
+    "ny_comm_init": ([_P, _I, _I, C.c_char_p, C.POINTER(_P)], _I),
+    "ny_comm_free": ([_P], None),
+    "ny_comm_size": ([_P], _I),
+    "ny_comm_rank": ([_P], _I),
+    "ny_comm_allreduce_host": ([_P, C.POINTER(_D), _I, _I, _P], _I),
+    "ny_halo_exchange": ([_P, _P, C.POINTER(_P), _I, ny_ext, _I, _I, _I, _I, _I, _P], _I),
+    "ny_mg_create_slab": ([_P, _P, _I, _I, _I, _I, C.POINTER(_P)], _I),
+    "ny_mg_is_box": ([_P], _I),
+    "ny_mg_set_fast_path": ([_P, _I], _I),
+    "ny_mg_first_gathered_level": ([_P], _I),
     "ny_mg_create": ([_P, _I, _I, _I, _I, C.POINTER(_P)], _I),
     "ny_mg_destroy": ([_P], None),
     "ny_mg_nlevels": ([_P], _I),

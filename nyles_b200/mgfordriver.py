@@ -20,7 +20,8 @@ def _tensor(a):
 class MG(object):
     IVAR = dict(x=1, b=2, r=3, y=4, diag=5, idiag=6, msk=7, Rcoef=8, Pcoef=9)
 
-    def __init__(self, npx, npy, nx, ny, nz, nh, topology=1, device=None):
+    def __init__(self, npx, npy, nx, ny, nz, nh, topology=1, device=None, npz=1):
+        """nx, ny, nz: LOCAL interior extents of this rank (as in the reference); npz slabs along z."""
         if npx != 1 or npy != 1:
             raise NotImplementedError("nyles_b200 decomposes along z only (npx = npy = 1)")
         if nh != 3:
@@ -30,7 +31,13 @@ class MG(object):
         self.ctx = lib.context(device)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         h = C.c_void_p()
-        lib.check(self.L.ny_mg_create(self.ctx, nx, ny, nz, topology, C.byref(h)))
+        if npz > 1:
+            from . import comm
+            if not comm.active() or self.L.ny_comm_size(comm.get()) != npz:
+                raise lib.NylesB200Error("npz = %d needs %d ranks (torchrun --nproc-per-node %d)" % (npz, npz, npz))
+            lib.check(self.L.ny_mg_create_slab(self.ctx, comm.get(), nx, ny, nz * npz, topology, C.byref(h)))
+        else:
+            lib.check(self.L.ny_mg_create(self.ctx, nx, ny, nz, topology, C.byref(h)))
         self.mg = h
         self.nlevels = self.L.ny_mg_nlevels(self.mg)
         self.shape = self.get_arrayshape()
@@ -116,6 +123,13 @@ class MG(object):
         else:
             _tensor(array).copy_(out)
         return array
+
+    def is_box(self):
+        return bool(self.L.ny_mg_is_box(self.mg))
+
+    def set_fast_path(self, on):
+        """on=False: generic kernels reading the coefficient arrays; on=True: fused box kernels."""
+        lib.check(self.L.ny_mg_set_fast_path(self.mg, 1 if on else 0))
 
     def op(self, name, lev=1):
         code = dict(smooth=1, residual=2, restriction=3, prolongation=4, vcycle=5)[name]

@@ -60,11 +60,8 @@ class LES(object):
         geometry = param["geometry"]
         if geometry not in TOPOLOGY or (self.euler and geometry == "perio_xy"):
             raise ValueError("geometry %r is not supported by the multigrid (model_les.py:80-88)" % geometry)
-        if param["npz"] > 1:
-            from .mg_slab import SlabMG
-            self.mg = SlabMG(param, grid, TOPOLOGY[geometry])
-        else:
-            self.mg = MG(grid.npx, grid.npy, param["nx"], param["ny"], param["nz"], param["nh"], TOPOLOGY[geometry])
+        self.mg = MG(grid.npx, grid.npy, param["nx"], param["ny"], param["nz"], param["nh"], TOPOLOGY[geometry],
+                     npz=param["npz"])
         self.mg.preallocate_for_nyles(grid.dx, param["neighbours"], self.halo)
         self.stats = []
 
