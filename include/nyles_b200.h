@@ -190,6 +190,9 @@ int  ny_mg_create(ny_ctx*, int nx, int ny, int nz, int topology, ny_mg** out);
  * (z halos filled from the neighbours through NCCL); small levels are gathered and solved
  * redundantly (mg_setup.f90:275-293).  Collective: every rank must make the same calls. */
 int  ny_mg_create_slab(ny_ctx*, ny_comm* comm, int nx, int ny, int nz_global, int topology, ny_mg** out);
+/* slab multigrids created afterwards gather every level with at most `cells` global cells
+ * (default 64^3); a level whose slab is thinner than 4 planes is gathered in any case */
+void ny_mg_set_gather_cells(long long cells);
 void ny_mg_destroy(ny_mg*);
 int  ny_mg_nlevels(ny_mg*);
 /* 1 if the mask is the default box, so that the fused analytic-coefficient kernels are in use */

@@ -31,6 +31,7 @@ namespace {
 constexpr int MAXLEV = 50;
 constexpr int NH = 3;
 constexpr int MAX_PARTIALS = 1 << 15;
+long long g_gather_cells = 262144;         // levels with at most this many cells are gathered (64^3)
 
 struct Level {
     int nx, ny, nz;                        // nz = local planes including the 2*nh halo planes
@@ -990,7 +991,7 @@ int create(ny_ctx* ctx, ny_comm* comm, int nx, int ny, int nz_global, int topolo
     mg->glev = 0;
     if (P > 1) {
         int l = 0;
-        while (l < mg->nlevels && gz[l] % P == 0 && gz[l] / P >= 4 && (long long)gx[l] * gy[l] * gz[l] > 262144LL) l++;
+        while (l < mg->nlevels && gz[l] % P == 0 && gz[l] / P >= 4 && (long long)gx[l] * gy[l] * gz[l] > g_gather_cells) l++;
         mg->glev = l;
         if (l == 0) {
             ny_set_error("ny_mg_create: the finest level (%dx%dx%d on %d slabs) is too small to be distributed",
@@ -1084,6 +1085,8 @@ extern "C" int ny_mg_create_slab(ny_ctx* ctx, ny_comm* comm, int nx, int ny, int
 {
     return create(ctx, comm, nx, ny, nz_global, topology, out);
 }
+
+extern "C" void ny_mg_set_gather_cells(long long cells) { g_gather_cells = cells; }
 
 extern "C" int ny_mg_nlevels(ny_mg* mg) { return mg ? mg->nlevels : 0; }
 extern "C" int ny_mg_is_box(ny_mg* mg) { return mg ? mg->box : 0; }

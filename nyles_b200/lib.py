@@ -72,6 +72,7 @@ _PROTOS = {
     "ny_comm_allreduce_host": ([_P, C.POINTER(_D), _I, _I, _P], _I),
     "ny_halo_exchange": ([_P, _P, C.POINTER(_P), _I, ny_ext, _I, _I, _I, _I, _I, _P], _I),
     "ny_mg_create_slab": ([_P, _P, _I, _I, _I, _I, C.POINTER(_P)], _I),
+    "ny_mg_set_gather_cells": ([_LL], None),
     "ny_mg_is_box": ([_P], _I),
     "ny_mg_set_fast_path": ([_P, _I], _I),
     "ny_mg_first_gathered_level": ([_P], _I),
