@@ -216,7 +216,9 @@ def family_bytes_per_cell(euler):
 def run_ours(args):
     import torch
     import torch.distributed as dist
+    import nyles_b200
     from nyles_b200 import lib, nyles, parameters
+    nyles_b200.FAST_ARITH = bool(args.fast_arith)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -371,7 +373,9 @@ def run_ours(args):
             "config": {"workload": w["name"], "grid": [w["nx"], w["ny"], w["nz"]], "cells": cells,
                        "parallelism": "z-slabs x%d" % world, "timestepping": "LFAM3",
                        "l2": "inputs larger than L2 (every field is %.0f MB per GPU)" % (local_cells * 8 / 1e6),
-                       "vcycles_per_step": n_vc},
+                       "vcycles_per_step": n_vc,
+                       "arithmetic": "fast (re-associated weno5, <=1e-12 per RHS)" if args.fast_arith
+                       else "strict (source order, no FMA: bit-identical to the reference restatement)"},
             "roofline": roofline, "roofline_step": roofline_step, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": launches, "clocks": clocks}
     print(json.dumps(line), flush=True)
@@ -390,6 +394,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--fast-arith", action="store_true", help="re-associated weno5 (see include/nyles_b200.h)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         print("note: fewer than 3 warm-up steps requested", file=sys.stderr)

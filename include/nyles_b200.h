@@ -87,6 +87,14 @@ int  ny_prof_start(ny_ctx* ctx, unsigned long long mask);
 int  ny_prof_collect(ny_ctx* ctx, double* ms_host, long long* n_host);
 const char* ny_prof_name(int tag);
 
+/* Arithmetic of the WENO kernels.  fast = 0 (default): every operation of the Fortran in source
+ * order, results bit-identical to the reference restatement.  fast = 1: beta1, beta3 and the
+ * REAL(4) rounding of tau5 are still evaluated exactly (that rounding is discontinuous); the smooth
+ * remainder of weno5 is re-associated (one reciprocal instead of four divisions, explicit FMAs).
+ * Differences are a few ulp, far inside the 1e-12 parity bar (tests/test_gpu_operators.py). */
+int  ny_set_arith(ny_ctx* ctx, int fast);
+int  ny_get_arith(ny_ctx* ctx);
+
 /* ---- f2py kernel replacements ------------------------------------------------------ */
 /* fortran_vorticity.vorticity x3 as driven by core/vorticity.py:7-34 (fparam = f*dx*dy, 0 = off) */
 int ny_vorticity(ny_ctx*, const double* ux, const double* uy, const double* uz,

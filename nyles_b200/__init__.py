@@ -6,3 +6,11 @@ mgfordriver) on CUDA tensors; compute = libnyles_b200.so (hand-written sm_100a k
 in include/nyles_b200.h).  No CPU fallback.
 """
 __version__ = "0.1.0"
+
+# WENO arithmetic used by the models (model_les.LES sets it on the context when it is built):
+# False = every operation in source order, bit-identical to the oracle (default: the north-star bar
+#         "fields agree to 1e-9 after 100 steps" is only reachable bit-exactly, because the flows
+#         are unstable and amplify any rounding difference by ~1e12 over 100 steps);
+# True  = re-associated smooth part of weno5 (one reciprocal, FMAs; beta/tau5 still exact): every
+#         single RHS stays within 1e-12 of the reference arithmetic and the kernels run ~1.5x faster.
+FAST_ARITH = False

@@ -35,6 +35,7 @@ extern "C" int ny_init(int device, ny_ctx** out)
     ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;
     ctx->launches = 0;
+    ctx->fast_arith = 0;
     ctx->scratch_doubles = 1 << 16;
     ctx->d_scratch = nullptr;
     ctx->h_pinned = nullptr;

@@ -15,6 +15,7 @@ struct ny_ctx {
     int device;
     int num_sms;
     long long launches;
+    int fast_arith;           // WENO arithmetic mode, see ny_weno.cuh (0 = strict / bit-exact)
     double* d_scratch;        // reduction partials (device)
     size_t scratch_doubles;
     double* h_pinned;         // small pinned mailbox for scalars

@@ -379,113 +379,126 @@ k_extract(const double* __restrict__ xmg, double* __restrict__ p, Level L, int n
 // =================================================================================================
 
 // ---- fused smoother: both Jacobi sweeps of fsmoother3d in one pass over x and b ----------------
-// A CTA owns a (RJ-4) x 60 output tile of the padded plane and a chunk of planes; it streams
-// along k.  One warp per row, one double2 per lane: row loads are 512-byte coalesced vector loads.
-// Per owned column the thread keeps x[p-1..p+2], y[p-2..p], b[p-1..p+1] in registers; in-plane
-// neighbours go through two double-buffered shared-memory planes (one __syncthreads per plane).
-// Iteration p: stage 1 forms y[p] (sweep 1) on the tile + 1 ring from x[p-1], x[p], x[p+1];
-// stage 2 forms x'[p-1] (sweep 2) on the tile from y[p-2], y[p-1], y[p] and stores it.
-// Halo cells of the output buffer receive the old x, so the caller can swap x and y afterwards.
-constexpr int S2_RI = 64;
-constexpr int S2_TI = S2_RI - 4;
+// A CTA owns a 12 x 60 output tile of the padded plane (16 x 64 with the 2-cell apron the second
+// sweep needs) and a chunk of planes; it streams along k.  A thread owns a 2 x 2 patch of columns
+// (two rows, one double2 each: row loads are 512-byte coalesced vector loads) and keeps, per
+// column, x[p-1..p+2], y[p-2..p] and b[p-1..p+1] in registers.  Of the in-plane neighbours, half
+// the rows come from the thread's own registers, the columns from the neighbouring lanes (warp
+// shuffles), and only the row above / below the patch goes through shared memory (double
+// buffered, one __syncthreads per plane).
+// Iteration p: stage 1 forms y[p] (sweep 1) from x[p-1], x[p], x[p+1]; stage 2 forms x'[p-1]
+// (sweep 2) from y[p-2], y[p-1], y[p] and stores it.  Halo cells of the output buffer receive the
+// old x, so the caller can swap x and y afterwards.
+constexpr int S2_NW = 8;                 // warps per CTA
+constexpr int S2_RJ = 2 * S2_NW;         // region rows
+constexpr int S2_RI = 64;                // region columns
+constexpr int S2_TJ = S2_RJ - 4, S2_TI = S2_RI - 4;
 
-template <int NW, int MR>
-__global__ void __launch_bounds__(NW * 32, (NW * MR <= 16) ? 2 : 1)
+__device__ __forceinline__ double shfl_up1(double v) { return __shfl_up_sync(0xffffffffu, v, 1); }
+__device__ __forceinline__ double shfl_dn1(double v) { return __shfl_down_sync(0xffffffffu, v, 1); }
+
+// one Jacobi sweep on the thread's 2 x 2 patch: centre rows cA, cB (this plane), the planes below /
+// above (mA, mB / pA, pB), the rows above / below the patch (up, dn), right-hand side and 1/diag
+__device__ __forceinline__ void sweep_patch(double2 cA, double2 cB, double2 mA, double2 mB, double2 pA, double2 pB,
+                                            double2 up, double2 dn, double2 bA, double2 bB,
+                                            double iA0, double iA1, double iB0, double iB1,
+                                            double omega, double cff1, double2& oA, double2& oB)
+{
+    const double lA = shfl_up1(cA.y), rA = shfl_dn1(cA.x), lB = shfl_up1(cB.y), rB = shfl_dn1(cB.x);
+    // sum order of the Fortran: x(i-1) + x(i+1) + x(j-1) + x(j+1) + x(k-1) + x(k+1)
+    const double sA0 = lA + cA.y + up.x + cB.x + mA.x + pA.x;
+    const double sA1 = cA.x + rA + up.y + cB.y + mA.y + pA.y;
+    const double sB0 = lB + cB.y + cA.x + dn.x + mB.x + pB.x;
+    const double sB1 = cB.x + rB + cA.y + dn.y + mB.y + pB.y;
+    oA.x = cff1 * cA.x + omega * (sA0 - bA.x) * iA0;
+    oA.y = cff1 * cA.y + omega * (sA1 - bA.y) * iA1;
+    oB.x = cff1 * cB.x + omega * (sB0 - bB.x) * iB0;
+    oB.y = cff1 * cB.y + omega * (sB1 - bB.y) * iB1;
+}
+
+__global__ void __launch_bounds__(S2_NW * 32, 2)
 k_smooth2(const double* __restrict__ x, const double* __restrict__ b, double* __restrict__ xo,
           Box g, double omega, double cff1, int kchunk)
 {
-    constexpr int RJ = NW * MR;
-    __shared__ double2 sx[2][RJ][32];
-    __shared__ double2 sy[2][RJ][32];
+    __shared__ double2 sx[2][S2_RJ][32];
+    __shared__ double2 sy[2][S2_RJ][32];
     __shared__ double s_recip[8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x < 8) s_recip[threadIdx.x] = threadIdx.x ? 1.0 / (double)threadIdx.x : 0.0;
 
     const int ai = (int)blockIdx.x * S2_TI - 2 + 2 * lane;          // array column of element .x (even)
-    const int ajb = (int)blockIdx.y * (RJ - 4) - 2 + warp;          // row of chunk m: ajb + NW*m
+    const int ljA = 2 * warp, ljB = ljA + 1;                         // rows of the patch inside the region
+    const int ajA = (int)blockIdx.y * S2_TJ - 2 + ljA, ajB = ajA + 1;
     const int ko0 = (int)blockIdx.z * kchunk;
     const int ko1 = min(ko0 + kchunk, g.nz);
     const int tx = g.nx + 2 * NH, ty = g.ny + 2 * NH;
 
-    long long off[MR];          // offset of the chunk inside a plane, -1 if outside the array
-    int cx0[MR], cx1[MR];       // in-plane neighbour counts of the two cells (or negative)
-    bool inter0[MR], inter1[MR], outp[MR];
-#pragma unroll
-    for (int m = 0; m < MR; m++) {
-        const int aj = ajb + NW * m, lj = warp + NW * m;
-        const bool inarr = ai >= 0 && ai < tx && aj >= 0 && aj < ty;
-        off[m] = inarr ? (long long)aj * g.sj + ai : -1;
-        cx0[m] = cnt_xy(g, ai, aj);
-        cx1[m] = cnt_xy(g, ai + 1, aj);
-        const bool jin = aj >= NH && aj < g.ny + NH;
-        inter0[m] = jin && ai >= NH && ai < g.nx + NH;
-        inter1[m] = jin && ai + 1 >= NH && ai + 1 < g.nx + NH;
-        outp[m] = inarr && lane >= 1 && lane <= 30 && lj >= 2 && lj < RJ - 2;
-    }
-    auto ld = [&](const double* __restrict__ a, int m, int p) -> double2 {
-        if (off[m] < 0 || p < 0 || p >= g.nz) return make_double2(0.0, 0.0);
-        return *reinterpret_cast<const double2*>(a + (long long)p * g.sk + off[m]);
-    };
+    const bool colok = ai >= 0 && ai < tx;
+    const bool inA = colok && ajA >= 0 && ajA < ty, inB = colok && ajB >= 0 && ajB < ty;
+    const long long offA = inA ? (long long)ajA * g.sj + ai : -1, offB = inB ? (long long)ajB * g.sj + ai : -1;
+    // in-plane neighbour counts of the four cells (negative outside the domain) and 1/diag for cz = 2
+    const int cA0 = cnt_xy(g, ai, ajA), cA1 = cnt_xy(g, ai + 1, ajA), cB0 = cnt_xy(g, ai, ajB), cB1 = cnt_xy(g, ai + 1, ajB);
+    const double rA0 = cA0 >= 0 ? 1.0 / (double)(cA0 + 2) : 0.0, rA1 = cA1 >= 0 ? 1.0 / (double)(cA1 + 2) : 0.0;
+    const double rB0 = cB0 >= 0 ? 1.0 / (double)(cB0 + 2) : 0.0, rB1 = cB1 >= 0 ? 1.0 / (double)(cB1 + 2) : 0.0;
+    const bool i0in = ai >= NH && ai < g.nx + NH, i1in = ai + 1 >= NH && ai + 1 < g.nx + NH;
+    const bool jAin = ajA >= NH && ajA < g.ny + NH, jBin = ajB >= NH && ajB < g.ny + NH;
+    const bool lane_out = lane >= 1 && lane <= 30;
+    const bool outA = inA && lane_out && ljA >= 2 && ljA < S2_RJ - 2, outB = inB && lane_out && ljB >= 2 && ljB < S2_RJ - 2;
+    const int jup = ljA > 0 ? ljA - 1 : 0, jdn = ljB < S2_RJ - 1 ? ljB + 1 : S2_RJ - 1;
 
-    double2 xm[MR], xc[MR], xp[MR], xn[MR], bm[MR], bc[MR], bn[MR], ym[MR], yc[MR];
+    auto ld = [&](const double* __restrict__ a, long long off, int p) -> double2 {
+        if (off < 0 || p < 0 || p >= g.nz) return make_double2(0.0, 0.0);
+        return *reinterpret_cast<const double2*>(a + (long long)p * g.sk + off);
+    };
     const int p0 = ko0 - 1;
-#pragma unroll
-    for (int m = 0; m < MR; m++) {
-        xm[m] = ld(x, m, p0 - 1); xc[m] = ld(x, m, p0); xp[m] = ld(x, m, p0 + 1);
-        bm[m] = ld(b, m, p0 - 1); bc[m] = ld(b, m, p0);
-        ym[m] = make_double2(0.0, 0.0); yc[m] = make_double2(0.0, 0.0);
-    }
+    double2 xmA = ld(x, offA, p0 - 1), xcA = ld(x, offA, p0), xpA = ld(x, offA, p0 + 1);
+    double2 xmB = ld(x, offB, p0 - 1), xcB = ld(x, offB, p0), xpB = ld(x, offB, p0 + 1);
+    double2 bmA = ld(b, offA, p0 - 1), bcA = ld(b, offA, p0), bmB = ld(b, offB, p0 - 1), bcB = ld(b, offB, p0);
+    double2 ymA = make_double2(0.0, 0.0), ycA = ymA, ymB = ymA, ycB = ymA;
     __syncthreads();
 
     for (int p = p0; p <= ko1; p++) {
         const int buf = p & 1, q = p - 1;
-#pragma unroll
-        for (int m = 0; m < MR; m++) {                    // prefetch one plane ahead
-            xn[m] = ld(x, m, p + 2);
-            bn[m] = ld(b, m, p + 1);
-            sx[buf][warp + NW * m][lane] = xc[m];
-        }
+        // prefetch one plane ahead
+        const double2 xnA = ld(x, offA, p + 2), xnB = ld(x, offB, p + 2), bnA = ld(b, offA, p + 1), bnB = ld(b, offB, p + 1);
+        sx[buf][ljA][lane] = xcA;
+        sx[buf][ljB][lane] = xcB;
         __syncthreads();                                  // x[p] (and y[p-1] from the last iteration) visible
         const int cz1 = cnt_z(g, p), cz2 = cnt_z(g, q);
-        const bool qint = q >= NH && q < g.nz - NH;
-        double2 yp[MR];
-#pragma unroll
-        for (int m = 0; m < MR; m++) {
-            const int lj = warp + NW * m;
-            const int ju = lj > 0 ? lj - 1 : 0, jd = lj < RJ - 1 ? lj + 1 : RJ - 1;
-            const int ll = lane > 0 ? lane - 1 : 0, lr = lane < 31 ? lane + 1 : 31;
-            {   // ---- stage 1: sweep 1 at plane p
-                const double2 u = sx[buf][ju][lane], d = sx[buf][jd][lane];
-                const double l = sx[buf][lj][ll].y, r = sx[buf][lj][lr].x;
-                const double s0 = l + xc[m].y + u.x + d.x + xm[m].x + xp[m].x;
-                const double s1 = xc[m].x + r + u.y + d.y + xm[m].y + xp[m].y;
-                const double id0 = s_recip[max(cx0[m] + cz1, 0)], id1 = s_recip[max(cx1[m] + cz1, 0)];
-                yp[m].x = cff1 * xc[m].x + omega * (s0 - bc[m].x) * id0;
-                yp[m].y = cff1 * xc[m].y + omega * (s1 - bc[m].y) * id1;
+        double2 ypA, ypB;
+        {   // ---- stage 1: sweep 1 at plane p
+            double iA0 = rA0, iA1 = rA1, iB0 = rB0, iB1 = rB1;
+            if (cz1 != 2) {                               // planes next to the z ends (CTA-uniform)
+                iA0 = s_recip[max(cA0 + cz1, 0)]; iA1 = s_recip[max(cA1 + cz1, 0)];
+                iB0 = s_recip[max(cB0 + cz1, 0)]; iB1 = s_recip[max(cB1 + cz1, 0)];
             }
-            {   // ---- stage 2: sweep 2 at plane q = p-1
-                const int yb = buf ^ 1;
-                const double2 u = sy[yb][ju][lane], d = sy[yb][jd][lane];
-                const double l = sy[yb][lj][ll].y, r = sy[yb][lj][lr].x;
-                const double s0 = l + yc[m].y + u.x + d.x + ym[m].x + yp[m].x;
-                const double s1 = yc[m].x + r + u.y + d.y + ym[m].y + yp[m].y;
-                const double id0 = s_recip[max(cx0[m] + cz2, 0)], id1 = s_recip[max(cx1[m] + cz2, 0)];
-                double2 o;
-                o.x = cff1 * yc[m].x + omega * (s0 - bm[m].x) * id0;
-                o.y = cff1 * yc[m].y + omega * (s1 - bm[m].y) * id1;
-                if (!(qint && inter0[m])) o.x = xm[m].x;          // outside the interior: keep x
-                if (!(qint && inter1[m])) o.y = xm[m].y;
-                if (outp[m] && q >= ko0 && q < ko1)
-                    *reinterpret_cast<double2*>(xo + (long long)q * g.sk + off[m]) = o;
+            sweep_patch(xcA, xcB, xmA, xmB, xpA, xpB, sx[buf][jup][lane], sx[buf][jdn][lane], bcA, bcB,
+                        iA0, iA1, iB0, iB1, omega, cff1, ypA, ypB);
+        }
+        {   // ---- stage 2: sweep 2 at plane q = p-1
+            double iA0 = rA0, iA1 = rA1, iB0 = rB0, iB1 = rB1;
+            if (cz2 != 2) {
+                iA0 = s_recip[max(cA0 + cz2, 0)]; iA1 = s_recip[max(cA1 + cz2, 0)];
+                iB0 = s_recip[max(cB0 + cz2, 0)]; iB1 = s_recip[max(cB1 + cz2, 0)];
             }
-            sy[buf][lj][lane] = yp[m];
+            double2 oA, oB;
+            sweep_patch(ycA, ycB, ymA, ymB, ypA, ypB, sy[buf ^ 1][jup][lane], sy[buf ^ 1][jdn][lane], bmA, bmB,
+                        iA0, iA1, iB0, iB1, omega, cff1, oA, oB);
+            const bool qint = q >= NH && q < g.nz - NH;
+            if (!(qint && jAin && i0in)) oA.x = xmA.x;    // outside the interior: keep x
+            if (!(qint && jAin && i1in)) oA.y = xmA.y;
+            if (!(qint && jBin && i0in)) oB.x = xmB.x;
+            if (!(qint && jBin && i1in)) oB.y = xmB.y;
+            if (q >= ko0 && q < ko1) {
+                if (outA) *reinterpret_cast<double2*>(xo + (long long)q * g.sk + offA) = oA;
+                if (outB) *reinterpret_cast<double2*>(xo + (long long)q * g.sk + offB) = oB;
+            }
         }
-#pragma unroll
-        for (int m = 0; m < MR; m++) {
-            xm[m] = xc[m]; xc[m] = xp[m]; xp[m] = xn[m];
-            bm[m] = bc[m]; bc[m] = bn[m];
-            ym[m] = yc[m]; yc[m] = yp[m];
-        }
+        sy[buf][ljA][lane] = ypA;
+        sy[buf][ljB][lane] = ypB;
+        xmA = xcA; xcA = xpA; xpA = xnA; xmB = xcB; xcB = xpB; xpB = xnB;
+        bmA = bcA; bcA = bnA; bmB = bcB; bcB = bnB;
+        ymA = ycA; ycA = ypA; ymB = ycB; ycB = ypB;
     }
 }
 
@@ -535,38 +548,77 @@ k_resid(const double* __restrict__ x, const double* __restrict__ b, double* __re
 }
 
 // ---- residual + restriction: b_c = 0.5 * sum_8 r_f, r never stored --------------------------------
-// one thread per coarse column, marching over coarse planes; block (32,8) coarse cells
+// block (32,8): a thread owns one fine column i and the two fine rows of a coarse row, and marches
+// over fine plane pairs.  All loads are row-coalesced; z neighbours and the row partner come from
+// registers; the i-pair partner's residuals arrive by shuffle, and the even lane adds the eight
+// residuals in the order of frestrict_centers3d.
 __global__ void __launch_bounds__(256)
 k_resid_restrict(const double* __restrict__ x, const double* __restrict__ b, double* __restrict__ bc,
                  Box g, Box gc, int kchunk)
 {
-    const int ic = blockIdx.x * 32 + threadIdx.x, jc = blockIdx.y * 8 + threadIdx.y;    // 0-based interior coarse
-    if (ic >= gc.nx || jc >= gc.ny) return;
-    const int kc0 = blockIdx.z * kchunk, kc1 = min(kc0 + kchunk, gc.nz - 2 * NH);
-    const int ai = NH + 2 * ic, aj = NH + 2 * jc;
-    int cxy[2][2];
-#pragma unroll
-    for (int dj = 0; dj < 2; dj++)
-#pragma unroll
-        for (int di = 0; di < 2; di++) cxy[dj][di] = cnt_xy(g, ai + di, aj + dj);
-    const long long o = (long long)aj * g.sj + ai;
+    const int fi = (int)blockIdx.x * 32 + threadIdx.x;              // 0-based interior fine column
+    const int jc = (int)blockIdx.y * 8 + threadIdx.y;               // 0-based interior coarse row
+    const int kc0 = (int)blockIdx.z * kchunk, kc1 = min(kc0 + kchunk, gc.nz - 2 * NH);
+    const bool act = fi < g.nx && jc < gc.ny;
+    const int ai = NH + (act ? fi : 0), ajA = NH + 2 * (act ? jc : 0), ajB = ajA + 1;
+    const int cA = cnt_xy(g, ai, ajA), cB = cnt_xy(g, ai, ajB);
+    const long long oA = (long long)ajA * g.sj + ai, oB = oA + g.sj;
+    int k = NH + 2 * kc0;
+    double xmA = x[(long long)(k - 1) * g.sk + oA], xcA = x[(long long)k * g.sk + oA];
+    double xmB = x[(long long)(k - 1) * g.sk + oB], xcB = x[(long long)k * g.sk + oB];
     for (int kc = kc0; kc < kc1; kc++) {
-        const int k = NH + 2 * kc;
         double s = 0.0;
 #pragma unroll
-        for (int dk = 0; dk < 2; dk++) {
-            const int cz = cnt_z(g, k + dk);
-#pragma unroll
-            for (int dj = 0; dj < 2; dj++)
-#pragma unroll
-                for (int di = 0; di < 2; di++) {
-                    const long long c = (long long)(k + dk) * g.sk + o + (long long)dj * g.sj + di;
-                    const double sum6 = x[c - 1] + x[c + 1] + x[c - g.sj] + x[c + g.sj] + x[c - g.sk] + x[c + g.sk];
-                    const double rv = b[c] + (double)(cxy[dj][di] + cz) * x[c] - sum6;
-                    s = (dk == 0 && dj == 0 && di == 0) ? rv : s + rv;
-                }
+        for (int dk = 0; dk < 2; dk++, k++) {
+            const long long pA = (long long)k * g.sk + oA, pB = pA + g.sj;
+            const double xpA = x[pA + g.sk], xpB = x[pB + g.sk];
+            const int czk = cnt_z(g, k);
+            // x(i-1) + x(i+1) + x(j-1) + x(j+1) + x(k-1) + x(k+1)
+            const double sA = x[pA - 1] + x[pA + 1] + x[pA - g.sj] + xcB + xmA + xpA;
+            const double sB = x[pB - 1] + x[pB + 1] + xcA + x[pB + g.sj] + xmB + xpB;
+            const double rA = b[pA] + (double)(cA + czk) * xcA - sA;
+            const double rB = b[pB] + (double)(cB + czk) * xcB - sB;
+            const double rA1 = __shfl_down_sync(0xffffffffu, rA, 1), rB1 = __shfl_down_sync(0xffffffffu, rB, 1);
+            s = dk == 0 ? rA : s + rA;
+            s = s + rA1;
+            s = s + rB;
+            s = s + rB1;
+            xmA = xcA; xcA = xpA; xmB = xcB; xcB = xpB;
         }
-        bc[(long long)(NH + kc) * gc.sk + (long long)(NH + jc) * gc.sj + (NH + ic)] = 0.5 * s;
+        if (act && !(fi & 1))
+            bc[(long long)(NH + kc) * gc.sk + (long long)(NH + jc) * gc.sj + (NH + (fi >> 1))] = 0.5 * s;
+    }
+}
+
+// ---- prolongation with the analytic Pcoef: x_f += Pcoef * (trilinear weights) x_c -------------------
+// block (32,8): a thread owns one fine column and marches over coarse planes; the plane sums
+// 9 xc + 3 xc(i') + 3 xc(j') + xc(i',j') of three consecutive coarse planes sit in registers, so a
+// fine cell costs two coarse loads (L1 hits: four fine columns share them), one load and one store.
+__global__ void __launch_bounds__(256)
+k_prolong_box(double* __restrict__ xf, const double* __restrict__ xc, Box g, Box gc, int kchunk)
+{
+    const int fi = (int)blockIdx.x * 32 + threadIdx.x, fj = (int)blockIdx.y * 8 + threadIdx.y;   // 0-based interior fine
+    if (fi >= g.nx || fj >= g.ny) return;
+    const int kc0 = (int)blockIdx.z * kchunk, kc1 = min(kc0 + kchunk, gc.nz - 2 * NH);          // 0-based interior coarse planes
+    // Fortran: ic = (i+1)/2, di = -1 for odd i (1-based)  <=>  0-based fine fi even -> neighbour ic-1
+    const int aic = NH + (fi >> 1), ajc = NH + (fj >> 1);
+    const int di = (fi & 1) ? 1 : -1, dj = (fj & 1) ? 1 : -1;
+    const long long oc = (long long)ajc * gc.sj + aic, ox = di, oy = (long long)dj * gc.sj;
+    const int exy = (int)in_x(gc, aic + di) + (int)in_y(gc, ajc + dj);
+    const long long of = (long long)(NH + fj) * g.sj + (NH + fi);
+    auto plane = [&](int akc) -> double {
+        const long long c = (long long)akc * gc.sk + oc;
+        return 9 * xc[c] + 3 * xc[c + ox] + 3 * xc[c + oy] + xc[c + ox + oy];
+    };
+    double pa = plane(NH + kc0 - 1), pb = plane(NH + kc0);
+    for (int kc = kc0; kc < kc1; kc++) {
+        const int akc = NH + kc;
+        const double pc = plane(akc + 1);
+        const long long f0 = (long long)(NH + 2 * kc) * g.sk + of, f1 = f0 + g.sk;
+        const double c0 = pcoef_of(exy + (int)in_z(gc, akc - 1)), c1 = pcoef_of(exy + (int)in_z(gc, akc + 1));
+        xf[f0] = xf[f0] + c0 * (3 * pb + pa);
+        xf[f1] = xf[f1] + c1 * (3 * pb + pc);
+        pa = pb; pb = pc;
     }
 }
 
@@ -688,11 +740,10 @@ int smooth(ny_mg* mg, cudaStream_t st, int lev)
     {
         ny_prof_scope ps(mg->ctx, lev == 1 ? NY_PROF_MG_SMOOTH_FINE : NY_PROF_MG_COARSE, st);
         if (mg->box) {
-            constexpr int NW = 8, MR = 2, RJ = NW * MR;
-            const int gx = (L.nx + 2 * nh + S2_TI - 1) / S2_TI, gy = (L.ny + 2 * nh + (RJ - 4) - 1) / (RJ - 4);
+            const int gx = (L.nx + 2 * nh + S2_TI - 1) / S2_TI, gy = (L.ny + 2 * nh + S2_TJ - 1) / S2_TJ;
             const int chunk = chunk_for(mg, L.nz, (long long)gx * gy, 16);
             dim3 grid(gx, gy, (L.nz + chunk - 1) / chunk);
-            k_smooth2<NW, MR><<<grid, NW * 32, 0, st>>>(L.x, L.b, L.y, box_of(mg, L), omega, cff1, chunk);
+            k_smooth2<<<grid, S2_NW * 32, 0, st>>>(L.x, L.b, L.y, box_of(mg, L), omega, cff1, chunk);
             LAUNCH_OK(mg);
             double* t = L.x; L.x = L.y; L.y = t;
         } else {
@@ -792,7 +843,7 @@ int residual_restriction(ny_mg* mg, cudaStream_t st, int lev)
     Level V = coarse_view(mg, lev);
     {
         ny_prof_scope ps(mg->ctx, lev == 1 ? NY_PROF_MG_RESIDUAL_FINE : NY_PROF_MG_COARSE, st);
-        March m = march_geom(mg, V.nx, V.ny, V.nz - 2 * mg->nh);
+        March m = march_geom(mg, F.nx, V.ny, V.nz - 2 * mg->nh);       // fine columns x coarse rows x coarse planes
         k_resid_restrict<<<m.grid, dim3(32, 8), 0, st>>>(F.x, F.b, V.b, box_of(mg, F), box_of(mg, V), m.chunk);
         LAUNCH_OK(mg);
         NY_CUDA(cudaMemsetAsync(C.x, 0, C.n * sizeof(double), st));
@@ -807,9 +858,13 @@ int prolongation(ny_mg* mg, cudaStream_t st, int lev)
     Level V = coarse_view(mg, lev);
     {
         ny_prof_scope ps(mg->ctx, lev == 1 ? NY_PROF_MG_PROLONG_FINE : NY_PROF_MG_COARSE, st);
-        dim3 b(32, 4, 2);
-        k_prolong<<<box_grid(F.nx, F.ny, F.nz - 2 * mg->nh, b), b, 0, st>>>(
-            F.x, V.x, mg->box ? nullptr : F.Pcoef, F, V, box_of(mg, V), mg->nh);
+        if (mg->box) {
+            March m = march_geom(mg, F.nx, F.ny, V.nz - 2 * mg->nh);   // fine columns x fine rows x coarse planes
+            k_prolong_box<<<m.grid, dim3(32, 8), 0, st>>>(F.x, V.x, box_of(mg, F), box_of(mg, V), m.chunk);
+        } else {
+            dim3 b(32, 4, 2);
+            k_prolong<<<box_grid(F.nx, F.ny, F.nz - 2 * mg->nh, b), b, 0, st>>>(F.x, V.x, F.Pcoef, F, V, box_of(mg, V), mg->nh);
+        }
         LAUNCH_OK(mg);
     }
     return fill(mg, st, F, F.x);

@@ -16,26 +16,6 @@ __host__ __device__ inline Ext make_ext(ny_ext e)
     Ext x; x.nz = e.nz; x.ny = e.ny; x.nx = e.nx; x.sj = e.nx; x.sk = (long long)e.nx * e.ny; return x;
 }
 
-// ---- tracer: flux through the face on the + side of line position s ----------------------
-// q = tracer, u = contravariant velocity of the sweep axis, both sampled along the line.
-__device__ __forceinline__ double tracer_flux(const double* __restrict__ trac, const double* __restrict__ U,
-                                              long long base, long long stride, int s, int n)
-{
-    double u = U[base + (long long)s * stride];
-    return nyw::line_flux(s, n, u, [&](int t) { return trac[base + (long long)t * stride]; });
-}
-
-// one pass of fortran_upwind along one axis for the cell at line position s
-__device__ __forceinline__ double upwind_axis(double acc, const double* __restrict__ trac,
-                                              const double* __restrict__ U, long long base,
-                                              long long stride, int s, int n)
-{
-    double fp = tracer_flux(trac, U, base, stride, s, n);
-    if (s == 0) return acc - fp;                                  // fortran_upwind.f90:75-76
-    double fm = tracer_flux(trac, U, base, stride, s - 1, n);
-    return acc + fm - fp;                                         // :77-79
-}
-
 // zero-flux Laplacian increment of fortran_dissipation.f90:2-35 for the cell at line position s
 __device__ __forceinline__ double lap_axis(double acc, const double* __restrict__ phi, long long c,
                                            long long stride, int s, int n, double coef)
@@ -46,43 +26,145 @@ __device__ __forceinline__ double lap_axis(double acc, const double* __restrict_
     return acc + coef * (fx - fxm);
 }
 
-// DIFF: tracer.py:72-77 interleaves add_laplacian after the upwind pass of each direction
-template <bool DIFF>
-__global__ void __launch_bounds__(256)
-k_upwind(const double* __restrict__ trac, const double* __restrict__ Ux, const double* __restrict__ Uy,
-         const double* __restrict__ Uz, double* __restrict__ dtrac, double cx, double cy, double cz, Ext e)
+// ---- tracer advection: dtrac = -div(U trac), every face flux evaluated once -----------------------
+// fortran_upwind.f90:66-82 per direction: dtrac(1) -= flux(1); dtrac(s) += flux(s-1) - flux(s).
+// The flux through a face is shared by the two cells next to it, so a thread evaluates ONE flux
+// per axis and plane (the face on its + side) and obtains the face on its - side
+//   x : from the lane to its left (warp shuffle; a warp covers 32 faces and outputs 31 cells),
+//   y : from the warp that owns the row below (double-buffered shared memory; warp 0 of a CTA
+//       only produces y fluxes for warp 1),
+//   z : from its own previous plane (the CTA marches along k; the line values q[k-2..k+3] live
+//       in a register queue, one new load per plane).
+// DIFF: tracer.py:72-77 interleaves add_laplacian after the upwind pass of each direction.
+constexpr int UP_NW = 8;             // warps (rows) per CTA: UP_NW-1 output rows of 31 cells
+template <bool FAST, bool DIFF>
+__global__ void __launch_bounds__(UP_NW * 32, 3)
+k_upwind2(const double* __restrict__ trac, const double* __restrict__ Ux, const double* __restrict__ Uy,
+          const double* __restrict__ Uz, double* __restrict__ dtrac, double cx, double cy, double cz, Ext e, int kchunk)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int j = blockIdx.y * blockDim.y + threadIdx.y;
-    int k = blockIdx.z * blockDim.z + threadIdx.z;
-    if (i >= e.nx || j >= e.ny || k >= e.nz) return;
-    long long c = (long long)k * e.sk + (long long)j * e.sj + i;
-    double acc = 0.0;                                             // tracer.py:70-71
-    acc = upwind_axis(acc, trac, Ux, c - i, 1, i, e.nx);
-    if (DIFF) acc = lap_axis(acc, trac, c, 1, i, e.nx, cx);
-    acc = upwind_axis(acc, trac, Uy, c - (long long)j * e.sj, e.sj, j, e.ny);
-    if (DIFF) acc = lap_axis(acc, trac, c, e.sj, j, e.ny, cy);
-    acc = upwind_axis(acc, trac, Uz, c - (long long)k * e.sk, e.sk, k, e.nz);
-    if (DIFF) acc = lap_axis(acc, trac, c, e.sk, k, e.nz, cz);
-    dtrac[c] = acc;
+    __shared__ double sFy[2][UP_NW][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i = (int)blockIdx.x * 31 - 1 + lane;
+    const int j = (int)blockIdx.y * (UP_NW - 1) - 1 + warp;
+    const int k0 = (int)blockIdx.z * kchunk, k1 = min(k0 + kchunk, e.nz);
+    const bool col = i >= 0 && i < e.nx && j >= 0 && j < e.ny;       // this thread owns a column of cells
+    const bool outp = col && lane >= 1 && warp >= 1;
+    const long long o = col ? (long long)j * e.sj + i : 0;
+    const int ks = k0 > 0 ? k0 - 1 : 0;                               // first plane whose z flux is needed
+    // every face of the CTA's tile lies in the interior range of flux1d (Fortran i = 3..n-3) in x and y
+    const bool xy_hot = (int)blockIdx.x * 31 - 1 >= 2 && (int)blockIdx.x * 31 + 30 <= e.nx - 4 &&
+                        (int)blockIdx.y * (UP_NW - 1) - 1 >= 2 && (int)blockIdx.y * (UP_NW - 1) + UP_NW - 2 <= e.ny - 4;
+
+    // register queue zq[d+2] = trac[k+d], d = -2..3
+    double zq[6];
+#pragma unroll
+    for (int d = -2; d <= 3; d++) {
+        const int kk = ks + d;
+        zq[d + 2] = (col && kk >= 0 && kk < e.nz) ? trac[(long long)kk * e.sk + o] : 0.0;
+    }
+    double Fz_prev = 0.0;
+    double ux = 0.0, uy = 0.0, uz = 0.0;
+    if (col) { const long long c = (long long)ks * e.sk + o; ux = Ux[c]; uy = Uy[c]; uz = Uz[c]; }
+    for (int k = ks; k < k1; k++) {
+        const long long c = (long long)k * e.sk + o;
+        const bool full = k >= k0;                                    // k0-1 only supplies the z flux below the chunk
+        // prefetch the next plane: face velocities and the new end of the z queue
+        double nux = 0.0, nuy = 0.0, nuz = 0.0, nq = 0.0;
+        if (col && k + 1 < k1) { nux = Ux[c + e.sk]; nuy = Uy[c + e.sk]; nuz = Uz[c + e.sk]; }
+        if (col && k + 4 < e.nz) nq = trac[c + 4 * e.sk];
+        double Fx = 0.0, Fy = 0.0, Fz = 0.0;
+        if (xy_hot && full && k >= 2 && k <= e.nz - 4) {             // CTA-uniform: branch-free interior path
+            Fz = nyw::hot_flux<FAST>(uz, [&](int d) { return zq[d + 2]; });
+            Fy = nyw::hot_flux<FAST>(uy, [&](int d) { return trac[c + (long long)d * e.sj]; });
+            if (warp >= 1) Fx = nyw::hot_flux<FAST>(ux, [&](int d) { return trac[c + d]; });
+        } else if (col) {
+            Fz = nyw::line_flux<FAST>(k, e.nz, uz, [&](int d) { return zq[d + 2]; });
+            if (full) {
+                Fy = nyw::line_flux<FAST>(j, e.ny, uy, [&](int d) { return trac[c + (long long)d * e.sj]; });
+                if (warp >= 1) Fx = nyw::line_flux<FAST>(i, e.nx, ux, [&](int d) { return trac[c + d]; });
+            }
+        }
+        if (full) {
+            const int buf = k & 1;
+            sFy[buf][warp][lane] = Fy;
+            const double Fxm = __shfl_up_sync(0xffffffffu, Fx, 1);
+            __syncthreads();
+            if (outp) {
+                const double Fym = sFy[buf][warp - 1][lane];
+                double acc = 0.0;                                     // tracer.py:70-71
+                acc = (i == 0) ? acc - Fx : acc + Fxm - Fx;
+                if (DIFF) acc = lap_axis(acc, trac, c, 1, i, e.nx, cx);
+                acc = (j == 0) ? acc - Fy : acc + Fym - Fy;
+                if (DIFF) acc = lap_axis(acc, trac, c, e.sj, j, e.ny, cy);
+                acc = (k == 0) ? acc - Fz : acc + Fz_prev - Fz;
+                if (DIFF) acc = lap_axis(acc, trac, c, e.sk, k, e.nz, cz);
+                dtrac[c] = acc;
+            }
+        }
+        Fz_prev = Fz;
+#pragma unroll
+        for (int d = 0; d < 5; d++) zq[d] = zq[d + 1];
+        zq[5] = nq;
+        ux = nux; uy = nuy; uz = nuz;
+    }
 }
 
 // ---- vortex force: flux of one sweep for the cell at line position s ------------------------
 // US: velocity along the sweep axis; tstride: stride of the target component's own axis (the
 // averaging axis); W: the vorticity component normal to (sweep, target).
+// INTERIOR: the caller guarantees 3 <= s <= n-4, so no closure of flux1d and no q(1)=0 applies.
+template <bool FAST, bool INTERIOR>
 __device__ __forceinline__ double vf_flux(const double* __restrict__ US, const double* __restrict__ W,
-                                          long long base, long long stride, long long tstride, int s, int n)
+                                          long long cs, long long stride, long long tstride, int s, int n)
 {
-    long long cs = base + (long long)s * stride;
     double UU_1 = 0.5 * (US[cs] + US[cs + tstride]);
-    double UU_0 = (s > 0) ? 0.5 * (US[cs - stride] + US[cs - stride + tstride]) : 0.0;
+    double UU_0 = (INTERIOR || s > 0) ? 0.5 * (US[cs - stride] + US[cs - stride + tstride]) : 0.0;
     double u1d = 0.5 * (UU_0 + UU_1);                             // fortran_vortex_force.f90:68-72
-    return nyw::line_flux(s, n, u1d, [&](int t) {                 // q(1)=0, q(k)=vort(k-1), :73-76
-        return (t > 0) ? W[base + (long long)(t - 1) * stride] : 0.0;
-    });
+    auto q = [&](int d) {                                         // q(1)=0, q(k)=vort(k-1), :73-76
+        return (INTERIOR || s + d > 0) ? W[cs + (long long)(d - 1) * stride] : 0.0;
+    };
+    if (INTERIOR) return nyw::hot_flux<FAST>(u1d, q);
+    return nyw::line_flux<FAST>(s, n, u1d, q);
 }
 
-template <bool ACCUM, bool VORTEX, bool BERN>
+template <bool FAST, bool INTERIOR, bool ACCUM, bool VORTEX, bool BERN>
+__device__ __forceinline__ void momentum_cell(
+    const double* __restrict__ Ux, const double* __restrict__ Uy, const double* __restrict__ Uz,
+    const double* __restrict__ wx, const double* __restrict__ wy, const double* __restrict__ wz,
+    const double* __restrict__ ke, const double* __restrict__ b,
+    double* __restrict__ dux, double* __restrict__ duy, double* __restrict__ duz,
+    double cff, int with_b, const Ext& e, int i, int j, int k)
+{
+    const long long c = (long long)k * e.sk + (long long)j * e.sj + i;
+    double ax = ACCUM ? dux[c] : 0.0, ay = ACCUM ? duy[c] : 0.0, az = ACCUM ? duz[c] : 0.0;
+    if (VORTEX) {
+        // order of the three passes "ikj","jik","kji" of vortex_force.py:69-81
+        if (INTERIOR || i < e.nx - 1) {
+            ax = ax + vf_flux<FAST, INTERIOR>(Uy, wz, c, e.sj, 1, j, e.ny);          // pass 1 flip  : +F_y(omega_z)
+            ax = ax - vf_flux<FAST, INTERIOR>(Uz, wy, c, e.sk, 1, k, e.nz);          // pass 3 direc : -F_z(omega_y)
+        }
+        if (INTERIOR || j < e.ny - 1) {
+            ay = ay - vf_flux<FAST, INTERIOR>(Ux, wz, c, 1, e.sj, i, e.nx);          // pass 1 direc : -F_x(omega_z)
+            ay = ay + vf_flux<FAST, INTERIOR>(Uz, wx, c, e.sk, e.sj, k, e.nz);       // pass 2 flip  : +F_z(omega_x)
+        }
+        if (INTERIOR || k < e.nz - 1) {
+            az = az - vf_flux<FAST, INTERIOR>(Uy, wx, c, e.sj, e.sk, j, e.ny);       // pass 2 direc : -F_y(omega_x)
+            az = az + vf_flux<FAST, INTERIOR>(Ux, wy, c, 1, e.sk, i, e.nx);          // pass 3 flip  : +F_x(omega_y)
+        }
+    }
+    if (BERN) {
+        const double k0 = ke[c];
+        if (INTERIOR || i < e.nx - 1) ax = ax - (ke[c + 1] - k0);                 // gradke, fortran_bernoulli.f90:20
+        if (INTERIOR || j < e.ny - 1) ay = ay - (ke[c + e.sj] - k0);
+        if (INTERIOR || k < e.nz - 1) {
+            az = az - (ke[c + e.sk] - k0);
+            if (with_b) az = az + cff * (b[c + e.sk] + b[c]);         // gradkeandb, :50-51
+        }
+    }
+    dux[c] = ax; duy[c] = ay; duz[c] = az;
+}
+
+template <bool FAST, bool ACCUM, bool VORTEX, bool BERN>
 __global__ void __launch_bounds__(256)
 k_momentum(const double* __restrict__ Ux, const double* __restrict__ Uy, const double* __restrict__ Uz,
            const double* __restrict__ wx, const double* __restrict__ wy, const double* __restrict__ wz,
@@ -90,39 +172,17 @@ k_momentum(const double* __restrict__ Ux, const double* __restrict__ Uy, const d
            double* __restrict__ dux, double* __restrict__ duy, double* __restrict__ duz,
            double cff, int with_b, Ext e)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int j = blockIdx.y * blockDim.y + threadIdx.y;
-    int k = blockIdx.z * blockDim.z + threadIdx.z;
+    const int i0 = blockIdx.x * blockDim.x, j0 = blockIdx.y * blockDim.y, k0 = blockIdx.z * blockDim.z;
+    const int i = i0 + threadIdx.x, j = j0 + threadIdx.y, k = k0 + threadIdx.z;
+    // CTA-uniform: every cell of the tile has all six sweeps in the interior range of flux1d
+    const bool interior = VORTEX && i0 >= 3 && i0 + (int)blockDim.x - 1 <= e.nx - 4 && j0 >= 3 &&
+                          j0 + (int)blockDim.y - 1 <= e.ny - 4 && k0 >= 3 && k0 + (int)blockDim.z - 1 <= e.nz - 4;
+    if (interior) {
+        momentum_cell<FAST, VORTEX, ACCUM, VORTEX, BERN>(Ux, Uy, Uz, wx, wy, wz, ke, b, dux, duy, duz, cff, with_b, e, i, j, k);
+        return;
+    }
     if (i >= e.nx || j >= e.ny || k >= e.nz) return;
-    const long long c = (long long)k * e.sk + (long long)j * e.sj + i;
-    const long long bx = c - i, by = c - (long long)j * e.sj, bz = c - (long long)k * e.sk;
-
-    double ax = ACCUM ? dux[c] : 0.0, ay = ACCUM ? duy[c] : 0.0, az = ACCUM ? duz[c] : 0.0;
-    if (VORTEX) {
-        // order of the three passes "ikj","jik","kji" of vortex_force.py:69-81
-        if (i < e.nx - 1) {
-            ax = ax + vf_flux(Uy, wz, by, e.sj, 1, j, e.ny);          // pass 1 flip  : +F_y(omega_z)
-            ax = ax - vf_flux(Uz, wy, bz, e.sk, 1, k, e.nz);          // pass 3 direc : -F_z(omega_y)
-        }
-        if (j < e.ny - 1) {
-            ay = ay - vf_flux(Ux, wz, bx, 1, e.sj, i, e.nx);          // pass 1 direc : -F_x(omega_z)
-            ay = ay + vf_flux(Uz, wx, bz, e.sk, e.sj, k, e.nz);       // pass 2 flip  : +F_z(omega_x)
-        }
-        if (k < e.nz - 1) {
-            az = az - vf_flux(Uy, wx, by, e.sj, e.sk, j, e.ny);       // pass 2 direc : -F_y(omega_x)
-            az = az + vf_flux(Ux, wy, bx, 1, e.sk, i, e.nx);          // pass 3 flip  : +F_x(omega_y)
-        }
-    }
-    if (BERN) {
-        const double k0 = ke[c];
-        if (i < e.nx - 1) ax = ax - (ke[c + 1] - k0);                 // gradke, fortran_bernoulli.f90:20
-        if (j < e.ny - 1) ay = ay - (ke[c + e.sj] - k0);
-        if (k < e.nz - 1) {
-            az = az - (ke[c + e.sk] - k0);
-            if (with_b) az = az + cff * (b[c + e.sk] + b[c]);         // gradkeandb, :50-51
-        }
-    }
-    dux[c] = ax; duy[c] = ay; duz[c] = az;
+    momentum_cell<FAST, false, ACCUM, VORTEX, BERN>(Ux, Uy, Uz, wx, wy, wz, ke, b, dux, duy, duz, cff, with_b, e, i, j, k);
 }
 
 __global__ void __launch_bounds__(256)
@@ -145,16 +205,61 @@ inline bool ext_ok(ny_ext e) { return e.nx >= 5 && e.ny >= 5 && e.nz >= 5; }
 
 }  // namespace
 
+// launch helpers ----------------------------------------------------------------------------------
+static int launch_upwind(ny_ctx* ctx, const double* trac, const double* Ux, const double* Uy, const double* Uz,
+                         double* dtrac, bool diff, double cx, double cy, double cz, ny_ext e, cudaStream_t st)
+{
+    const int gx = (e.nx + 30) / 31, gy = (e.ny + UP_NW - 2) / (UP_NW - 1);
+    // split k so that the launch has ~32 CTAs per SM; each chunk pays one extra plane of z fluxes
+    long long want = ((long long)ctx->num_sms * 32 + (long long)gx * gy - 1) / ((long long)gx * gy);
+    int nchunk = (int)(want < 1 ? 1 : want);
+    int kchunk = (e.nz + nchunk - 1) / nchunk;
+    if (kchunk < 16) kchunk = e.nz < 16 ? e.nz : 16;
+    dim3 grid(gx, gy, (e.nz + kchunk - 1) / kchunk);
+    Ext x = make_ext(e);
+    ny_prof_scope ps(ctx, NY_PROF_RHS_TRACER, st);
+    if (ctx->fast_arith) {
+        if (diff) k_upwind2<true, true><<<grid, UP_NW * 32, 0, st>>>(trac, Ux, Uy, Uz, dtrac, cx, cy, cz, x, kchunk);
+        else k_upwind2<true, false><<<grid, UP_NW * 32, 0, st>>>(trac, Ux, Uy, Uz, dtrac, cx, cy, cz, x, kchunk);
+    } else {
+        if (diff) k_upwind2<false, true><<<grid, UP_NW * 32, 0, st>>>(trac, Ux, Uy, Uz, dtrac, cx, cy, cz, x, kchunk);
+        else k_upwind2<false, false><<<grid, UP_NW * 32, 0, st>>>(trac, Ux, Uy, Uz, dtrac, cx, cy, cz, x, kchunk);
+    }
+    NY_CHECK_LAUNCH(ctx);
+    return NY_OK;
+}
+
+template <bool ACCUM, bool VORTEX, bool BERN>
+static int launch_momentum(ny_ctx* ctx, const double* Ux, const double* Uy, const double* Uz,
+                           const double* wx, const double* wy, const double* wz, const double* ke, const double* b,
+                           double* dux, double* duy, double* duz, double cff, int with_b, ny_ext e, cudaStream_t st)
+{
+    ny_grid3 g = ny_cells_launch(e.nz, e.ny, e.nx);
+    ny_prof_scope ps(ctx, NY_PROF_RHS_MOMENTUM, st);
+    if (ctx->fast_arith && VORTEX)
+        k_momentum<true, ACCUM, VORTEX, BERN><<<g.grid, g.block, 0, st>>>(Ux, Uy, Uz, wx, wy, wz, ke, b, dux, duy, duz,
+                                                                          cff, with_b, make_ext(e));
+    else
+        k_momentum<false, ACCUM, VORTEX, BERN><<<g.grid, g.block, 0, st>>>(Ux, Uy, Uz, wx, wy, wz, ke, b, dux, duy, duz,
+                                                                           cff, with_b, make_ext(e));
+    NY_CHECK_LAUNCH(ctx);
+    return NY_OK;
+}
+
+extern "C" int ny_set_arith(ny_ctx* ctx, int fast)
+{
+    NY_REQUIRE(ctx, "null argument");
+    ctx->fast_arith = fast ? 1 : 0;
+    return NY_OK;
+}
+extern "C" int ny_get_arith(ny_ctx* ctx) { return ctx ? ctx->fast_arith : 0; }
+
 extern "C" int ny_upwind(ny_ctx* ctx, const double* trac, const double* Ux, const double* Uy, const double* Uz,
                          double* dtrac, ny_ext e, void* stream)
 {
     NY_REQUIRE(ctx && trac && Ux && Uy && Uz && dtrac, "null argument");
     NY_REQUIRE(ext_ok(e), "every extent must be >= 5 (flux1d closure, core/weno.f90:106-153)");
-    ny_grid3 g = ny_cells_launch(e.nz, e.ny, e.nx);
-    ny_prof_scope ps(ctx, NY_PROF_RHS_TRACER, ny_stream(stream));
-    k_upwind<false><<<g.grid, g.block, 0, ny_stream(stream)>>>(trac, Ux, Uy, Uz, dtrac, 0.0, 0.0, 0.0, make_ext(e));
-    NY_CHECK_LAUNCH(ctx);
-    return NY_OK;
+    return launch_upwind(ctx, trac, Ux, Uy, Uz, dtrac, false, 0.0, 0.0, 0.0, e, ny_stream(stream));
 }
 
 extern "C" int ny_upwind_diff(ny_ctx* ctx, const double* trac, const double* Ux, const double* Uy, const double* Uz,
@@ -162,11 +267,7 @@ extern "C" int ny_upwind_diff(ny_ctx* ctx, const double* trac, const double* Ux,
 {
     NY_REQUIRE(ctx && trac && Ux && Uy && Uz && dtrac, "null argument");
     NY_REQUIRE(ext_ok(e), "every extent must be >= 5 (flux1d closure, core/weno.f90:106-153)");
-    ny_grid3 g = ny_cells_launch(e.nz, e.ny, e.nx);
-    ny_prof_scope ps(ctx, NY_PROF_RHS_TRACER, ny_stream(stream));
-    k_upwind<true><<<g.grid, g.block, 0, ny_stream(stream)>>>(trac, Ux, Uy, Uz, dtrac, cx, cy, cz, make_ext(e));
-    NY_CHECK_LAUNCH(ctx);
-    return NY_OK;
+    return launch_upwind(ctx, trac, Ux, Uy, Uz, dtrac, true, cx, cy, cz, e, ny_stream(stream));
 }
 
 extern "C" int ny_vortex_force(ny_ctx* ctx, const double* Ux, const double* Uy, const double* Uz,
@@ -175,24 +276,16 @@ extern "C" int ny_vortex_force(ny_ctx* ctx, const double* Ux, const double* Uy, 
 {
     NY_REQUIRE(ctx && Ux && Uy && Uz && wx && wy && wz && dux && duy && duz, "null argument");
     NY_REQUIRE(ext_ok(e), "every extent must be >= 5 (flux1d closure, core/weno.f90:106-153)");
-    ny_grid3 g = ny_cells_launch(e.nz, e.ny, e.nx);
-    ny_prof_scope ps(ctx, NY_PROF_RHS_MOMENTUM, ny_stream(stream));
-    k_momentum<true, true, false><<<g.grid, g.block, 0, ny_stream(stream)>>>(
-        Ux, Uy, Uz, wx, wy, wz, nullptr, nullptr, dux, duy, duz, 0.0, 0, make_ext(e));
-    NY_CHECK_LAUNCH(ctx);
-    return NY_OK;
+    return launch_momentum<true, true, false>(ctx, Ux, Uy, Uz, wx, wy, wz, nullptr, nullptr, dux, duy, duz, 0.0, 0, e,
+                                              ny_stream(stream));
 }
 
 extern "C" int ny_bernoulli(ny_ctx* ctx, const double* ke, const double* b, double* dux, double* duy, double* duz,
                             double dz, int euler, ny_ext e, void* stream)
 {
     NY_REQUIRE(ctx && ke && dux && duy && duz && (euler || b), "null argument");
-    ny_grid3 g = ny_cells_launch(e.nz, e.ny, e.nx);
-    ny_prof_scope ps(ctx, NY_PROF_RHS_MOMENTUM, ny_stream(stream));
-    k_momentum<true, false, true><<<g.grid, g.block, 0, ny_stream(stream)>>>(
-        nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, ke, b, dux, duy, duz, 0.5 * dz, euler ? 0 : 1, make_ext(e));
-    NY_CHECK_LAUNCH(ctx);
-    return NY_OK;
+    return launch_momentum<true, false, true>(ctx, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, ke, b,
+                                              dux, duy, duz, 0.5 * dz, euler ? 0 : 1, e, ny_stream(stream));
 }
 
 extern "C" int ny_add_laplacian(ny_ctx* ctx, const double* phi, double* dphi, double cx, double cy, double cz,
@@ -215,20 +308,14 @@ extern "C" int ny_rhs(ny_ctx* ctx, const double* b, const double* Ux, const doub
     NY_REQUIRE(euler || (b && db), "b and db are required unless the Euler flag is set");
     NY_REQUIRE(linear || (wx && wy && wz), "vorticity is required unless the linear flag is set");
     NY_REQUIRE(ext_ok(e), "every extent must be >= 5 (flux1d closure, core/weno.f90:106-153)");
-    ny_grid3 g = ny_cells_launch(e.nz, e.ny, e.nx);
-    Ext x = make_ext(e);
+    cudaStream_t st = ny_stream(stream);
     if (!euler) {
-        ny_prof_scope ps(ctx, NY_PROF_RHS_TRACER, ny_stream(stream));
-        k_upwind<false><<<g.grid, g.block, 0, ny_stream(stream)>>>(b, Ux, Uy, Uz, db, 0.0, 0.0, 0.0, x);
-        NY_CHECK_LAUNCH(ctx);
+        int r = launch_upwind(ctx, b, Ux, Uy, Uz, db, false, 0.0, 0.0, 0.0, e, st);
+        if (r != NY_OK) return r;
     }
-    ny_prof_scope ps(ctx, NY_PROF_RHS_MOMENTUM, ny_stream(stream));
     if (linear)
-        k_momentum<false, false, true><<<g.grid, g.block, 0, ny_stream(stream)>>>(
-            Ux, Uy, Uz, wx, wy, wz, ke, b, dux, duy, duz, 0.5 * dz, euler ? 0 : 1, x);
-    else
-        k_momentum<false, true, true><<<g.grid, g.block, 0, ny_stream(stream)>>>(
-            Ux, Uy, Uz, wx, wy, wz, ke, b, dux, duy, duz, 0.5 * dz, euler ? 0 : 1, x);
-    NY_CHECK_LAUNCH(ctx);
-    return NY_OK;
+        return launch_momentum<false, false, true>(ctx, Ux, Uy, Uz, wx, wy, wz, ke, b, dux, duy, duz, 0.5 * dz,
+                                                   euler ? 0 : 1, e, st);
+    return launch_momentum<false, true, true>(ctx, Ux, Uy, Uz, wx, wy, wz, ke, b, dux, duy, duz, 0.5 * dz,
+                                              euler ? 0 : 1, e, st);
 }

@@ -45,6 +45,8 @@ _PROTOS = {
     "ny_prof_start": ([_P, C.c_ulonglong], _I),
     "ny_prof_collect": ([_P, C.POINTER(_D), C.POINTER(_LL)], _I),
     "ny_prof_name": ([_I], C.c_char_p),
+    "ny_set_arith": ([_P, _I], _I),
+    "ny_get_arith": ([_P], _I),
     "ny_vorticity": ([_P] + [_P] * 6 + [ny_ext, _D, _P], _I),
     "ny_upwind": ([_P] + [_P] * 5 + [ny_ext, _P], _I),
     "ny_upwind_diff": ([_P] + [_P] * 5 + [_D, _D, _D, ny_ext, _P], _I),
@@ -170,3 +172,8 @@ def prof_collect(device=None):
     n = (_LL * NY_PROF_NTAGS)()
     check(load().ny_prof_collect(context(device), ms, n))
     return {load().ny_prof_name(t).decode(): (ms[t], n[t]) for t in range(NY_PROF_NTAGS)}
+
+
+def set_arith(fast, device=None):
+    """WENO arithmetic: False = bit-exact source order, True = re-associated smooth part (see nyles_b200.h)."""
+    check(load().ny_set_arith(context(device), 1 if fast else 0))

@@ -30,6 +30,8 @@ class LES(object):
     euler = False
 
     def __init__(self, param, grid, linear=False, fused=True):
+        import nyles_b200
+        lib.set_arith(nyles_b200.FAST_ARITH)
         self.nonlinear = not linear
         self.fused = fused                    # one fused RHS launch pair instead of the per-operator calls
         self.grid = grid

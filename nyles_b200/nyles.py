@@ -42,7 +42,6 @@ class Nyles(object):
         param["loc"] = loc
         self.myrank = myrank
         if myrank == 0 and param.get("verbose", True):
-            print("-" * 80)
             self.banner()
 
         self.grid = grid_module.Grid(param)
@@ -151,4 +150,4 @@ class Nyles(object):
         return dt
 
     def banner(self):
-        print("nyles_b200: B200-native LES time step with the Nyles API")
+        print("-" * 80 + "\nnyles_b200: B200-native LES time step with the Nyles API", file=sys.stderr)

@@ -95,9 +95,18 @@ def lock_exchange_ic(shape, x, dx):
     return np.tanh((x + noise - 8) / (2 * dx))
 
 
-def test_lock_exchange_100_steps_vs_oracle():
+@pytest.mark.parametrize("fast_arith", [False, True])
+def test_lock_exchange_100_steps_vs_oracle(fast_arith, monkeypatch):
     """BASELINE config 0: experiments/lockechange/lockexchange.py at its default grid (128x32x32,
-    closed, LES, LFAM3, cfl 0.8, dt_max 0.1), 100 steps, GPU against the oracle."""
+    closed, LES, LFAM3, cfl 0.8, dt_max 0.1), 100 steps, GPU against the oracle.
+    Strict arithmetic: dt agrees to 1e-12 at every step.  Fast arithmetic (the models' default): the
+    few-ulp differences of the RHS accumulate, dt is held to the same 1e-9 as the fields."""
+    import nyles_b200
+    monkeypatch.setattr(nyles_b200, "FAST_ARITH", fast_arith)
+    # fast mode: the lock exchange is unstable (Kelvin-Helmholtz billows), a few-ulp change of the RHS
+    # grows by ~1e3 every 28 steps; it is compared over the first 20 steps only
+    dt_tol = 1e-10 if fast_arith else 1e-12
+    nsteps = 20 if fast_arith else 100
     kw = dict(nx=128, ny=32, nz=32, geometry="closed", Lx=32.0, Ly=8.0, Lz=8.0, cfl=0.8, dt_max=0.1)
     o = M.LES(M.make_param(**kw))
     ny = make_nyles(kw)
@@ -110,10 +119,10 @@ def test_lock_exchange_100_steps_vs_oracle():
     ny.model.diagnose_var(ny.model.state)
     t = 0.0
     gpu_cycles = []
-    for n in range(100):
+    for n in range(nsteps):
         dt_o = o.compute_dt()
         dt_g = ny.compute_dt()
-        assert abs(dt_o - dt_g) <= 1e-12 * dt_o, "dt differs at step %d" % n
+        assert abs(dt_o - dt_g) <= dt_tol * dt_o, "dt differs at step %d" % n
         before = ny.model.mg.nvcycles
         o.forward(t, dt_o)
         ny.model.forward(t, dt_g)
@@ -125,7 +134,7 @@ def test_lock_exchange_100_steps_vs_oracle():
     assert relerr(st.b.tensor.cpu().numpy(), o.state.b.data) <= 1e-9
     for d in "ijk":
         assert relerr(st.u[d].tensor.cpu().numpy(), o.state.u[d].data) <= 1e-9
-    assert float(st.u["i"].tensor.abs().max()) > 0.05          # the current actually developed
+    assert float(st.u["i"].tensor.abs().max()) > (0.05 if nsteps == 100 else 0.005)      # the current actually developed
 
 
 def test_tracer_conservation_and_projection_properties_large():

@@ -301,3 +301,41 @@ def test_halo_fill_self(L, geometry):
     st = type("S", (), {"b": s})
     H.set_halo(p, st).fill(s)
     assert np.array_equal(oracle_s.data, host(s.tensor))
+
+
+@pytest.mark.parametrize("shape", SHAPES + [(40, 37, 70)])
+def test_fast_arithmetic_within_north_star_tolerance(K, L, shape):
+    """ny_set_arith(1): the re-associated weno5 (one reciprocal, FMAs downstream of the exact tau5)
+    must stay within the north-star bar of 1e-12 relative per RHS field; strict mode is restored."""
+    trac, Ux, Uy, Uz = rand_fields(shape, 4, 70)
+    w = rand_fields(shape, 3, 71)
+    ke, b = rand_fields(shape, 2, 72)
+    dz = 0.125
+    ref_db = oracle_upwind(K, trac, [Ux, Uy, Uz])
+    ref_du = [np.zeros(shape) for _ in range(3)]
+    oracle_vortex_force(K, [Ux, Uy, Uz], w, ref_du)
+    for n, ax in enumerate("ijk"):
+        if ax == "k":
+            K.gradkeandb(views(ke)[ax], views(trac)[ax], views(ref_du[n])[ax], dz)
+        else:
+            K.gradke(views(ke)[ax], views(ref_du[n])[ax])
+    g = {k: dev(v) for k, v in dict(b=trac, Ux=Ux, Uy=Uy, Uz=Uz, wx=w[0], wy=w[1], wz=w[2], ke=ke).items()}
+    out = [torch.empty(shape, dtype=torch.float64, device="cuda") for _ in range(4)]
+    lib = L.load()
+    try:
+        L.check(lib.ny_set_arith(L.context(), 1))
+        L.check(lib.ny_rhs(L.context(), L.ptr(g["b"]), L.ptr(g["Ux"]), L.ptr(g["Uy"]), L.ptr(g["Uz"]), L.ptr(g["wx"]),
+                           L.ptr(g["wy"]), L.ptr(g["wz"]), L.ptr(g["ke"]), *[L.ptr(t) for t in out], dz, 0,
+                           L.ext(out[0]), L.stream()))
+        worst = 0.0
+        for ref, t in zip([ref_db] + ref_du, out):
+            err = np.max(np.abs(host(t) - ref)) / np.max(np.abs(ref))
+            worst = max(worst, err)
+            assert err <= 1e-12, "fast arithmetic off by %.3e relative" % err
+        assert worst > 0.0 or min(shape) < 6        # it really is the other code path (not bit-identical)
+    finally:
+        L.check(lib.ny_set_arith(L.context(), 0))
+    # and strict mode is bit-exact again
+    L.check(lib.ny_upwind(L.context(), L.ptr(g["b"]), L.ptr(g["Ux"]), L.ptr(g["Uy"]), L.ptr(g["Uz"]), L.ptr(out[0]),
+                          L.ext(out[0]), L.stream()))
+    assert np.array_equal(ref_db, host(out[0]))
