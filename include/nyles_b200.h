@@ -149,6 +149,11 @@ int ny_rhs(ny_ctx*, const double* b, const double* Ux, const double* Uy, const d
            double* db, double* dux, double* duy, double* duz,
            double dz, int flags, ny_ext e, void* stream);
 
+/* U_from_u + vorticity + kinenergy (core/model_les.py:112-123) in one pass over u */
+int ny_diag_post(ny_ctx*, const double* ux, const double* uy, const double* uz,
+                 double* Ux, double* Uy, double* Uz, double* wx, double* wy, double* wz, double* ke,
+                 double idx2, double idy2, double idz2, double fparam, ny_ext e, void* stream);
+
 /* ---- time schemes (core/timescheme.py:113-221), n = number of doubles ------------------ */
 int ny_ts_axpy(ny_ctx*, double* s, const double* ds, double a, long long n, void* stream);     /* s += a*ds */
 int ny_ts_lfam3_first(ny_ctx*, double* s, const double* ds, double* sb, double* sn, double dt,
@@ -224,6 +229,13 @@ int  ny_mg_solve(ny_mg*, ny_mg_stats* stats_host, void* stream);
  * inside the padded MG array (nh on sides without neighbour, 0 on sides with). */
 int  ny_mg_solve_directly(ny_mg*, double* p, const double* div, ny_ext e, const int lo[3],
                           double scale, ny_mg_stats* stats_host, void* stream);
+/* projection.compute_p (core/projection.py:39-87) around the in-place solve: div = delta(u*ids2) is
+ * written to `div` and embedded in b (then halo-filled there, which is what halo.fill(div) achieves in
+ * the reference), solve, p = x*scale, u -= delta p.  The halo cells of the model's `div` array are not
+ * refreshed. */
+int  ny_mg_project(ny_mg*, double* ux, double* uy, double* uz, double* div, double* p,
+                   double idx2, double idy2, double idz2, ny_ext e, const int lo[3], double scale,
+                   ny_mg_stats* stats_host, void* stream);
 int  ny_mg_op(ny_mg*, int op, int lev, void* stream);
 
 #ifdef __cplusplus

@@ -59,6 +59,33 @@ k_kin(const double* __restrict__ ux, const double* __restrict__ uy, const double
     ke[c] = acc;
 }
 
+// U_from_u + vorticity + kinenergy in one pass over u (same statements as k_scale3, k_vorticity, k_kin)
+__global__ void __launch_bounds__(256)
+k_diag_post(const double* __restrict__ ux, const double* __restrict__ uy, const double* __restrict__ uz,
+            double* __restrict__ Ux, double* __restrict__ Uy, double* __restrict__ Uz,
+            double* __restrict__ wx, double* __restrict__ wy, double* __restrict__ wz, double* __restrict__ ke,
+            double idx2, double idy2, double idz2, double cx, double cy, double cz, double fparam, Ext e)
+{
+    CELL_INDEX
+    const double u0 = ux[c], v0 = uy[c], w0 = uz[c];
+    Ux[c] = u0 * idx2; Uy[c] = v0 * idy2; Uz[c] = w0 * idz2;
+    const bool ip = i < e.nx - 1, jp = j < e.ny - 1, kp = k < e.nz - 1;
+    if (kp) wx[c] = jp ? uz[c + e.sj] - w0 - uy[c + e.sk] + v0 : 0.0;
+    if (ip) wy[c] = kp ? ux[c + e.sk] - u0 - uz[c + 1] + w0 : 0.0;
+    if (jp) {
+        if (ip) {
+            double w = uy[c + 1] - v0 - ux[c + e.sj] + u0;
+            if (fparam > 0.0) w = w + fparam;
+            wz[c] = w;
+        } else wz[c] = 0.0;
+    }
+    double acc = 0.0;
+    if (i > 0) { double q = ux[c - 1]; acc = acc + cx * (u0 * u0 + q * q); }
+    if (j > 0) { double q = uy[c - e.sj]; acc = acc + cy * (v0 * v0 + q * q); }
+    if (k > 0) { double q = uz[c - e.sk]; acc = acc + cz * (w0 * w0 + q * q); }
+    ke[c] = acc;
+}
+
 __global__ void __launch_bounds__(256)
 k_div(const double* __restrict__ Ux, const double* __restrict__ Uy, const double* __restrict__ Uz,
       double* __restrict__ div, Ext e)
@@ -217,6 +244,20 @@ extern "C" int ny_kin(ny_ctx* ctx, const double* ux, const double* uy, const dou
     ny_prof_scope ps(ctx, NY_PROF_VORT_KE, ny_stream(stream));
     k_kin<<<g.grid, g.block, 0, ny_stream(stream)>>>(ux, uy, uz, ke, (0.5 * idx2) * 0.5, (0.5 * idy2) * 0.5,
                                                       (0.5 * idz2) * 0.5, make_ext(e));
+    NY_CHECK_LAUNCH(ctx);
+    return NY_OK;
+}
+
+extern "C" int ny_diag_post(ny_ctx* ctx, const double* ux, const double* uy, const double* uz,
+                            double* Ux, double* Uy, double* Uz, double* wx, double* wy, double* wz, double* ke,
+                            double idx2, double idy2, double idz2, double fparam, ny_ext e, void* stream)
+{
+    NY_REQUIRE(ctx && ux && uy && uz && Ux && Uy && Uz && wx && wy && wz && ke, "null argument");
+    ny_grid3 g = ny_cells_launch(e.nz, e.ny, e.nx);
+    ny_prof_scope ps(ctx, NY_PROF_VORT_KE, ny_stream(stream));
+    k_diag_post<<<g.grid, g.block, 0, ny_stream(stream)>>>(ux, uy, uz, Ux, Uy, Uz, wx, wy, wz, ke, idx2, idy2, idz2,
+                                                           (0.5 * idx2) * 0.5, (0.5 * idy2) * 0.5, (0.5 * idz2) * 0.5,
+                                                           fparam, make_ext(e));
     NY_CHECK_LAUNCH(ctx);
     return NY_OK;
 }

@@ -374,6 +374,45 @@ k_extract(const double* __restrict__ xmg, double* __restrict__ p, Level L, int n
         xmg[(long long)(k + k0) * L.sk + (long long)(j + j0) * L.sj + (i + i0)] * scale;
 }
 
+// fused forms of the projection glue (core/projection.py:39-87 + core/mgfordriver.py:66-78):
+// U = u*ids2 on the fly, div = delta U (fortran_bernoulli.f90:61-97), stored in the model's div array
+// and embedded in the right-hand side of the finest level
+__global__ void __launch_bounds__(256)
+k_div_embed(const double* __restrict__ ux, const double* __restrict__ uy, const double* __restrict__ uz,
+            double* __restrict__ div, double* __restrict__ bmg, double idx2, double idy2, double idz2,
+            Level L, int nz, int ny, int nx, int k0, int j0, int i0)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int j = blockIdx.y * blockDim.y + threadIdx.y;
+    int k = blockIdx.z * blockDim.z + threadIdx.z;
+    if (i >= nx || j >= ny || k >= nz) return;
+    const long long sj = nx, sk = (long long)nx * ny, c = (long long)k * sk + (long long)j * sj + i;
+    const double U0 = ux[c] * idx2, V0 = uy[c] * idy2, W0 = uz[c] * idz2;
+    double d = (i > 0) ? (U0 - ux[c - 1] * idx2) : U0;
+    d = (j > 0) ? d + (V0 - uy[c - sj] * idy2) : d + V0;
+    d = (k > 0) ? d + (W0 - uz[c - sk] * idz2) : d + W0;
+    div[c] = d;
+    bmg[(long long)(k + k0) * L.sk + (long long)(j + j0) * L.sj + (i + i0)] = d;
+}
+// p = x*scale over the model array, u -= delta p (fortran_bernoulli.f90:2-26 as called by projection.py:84-87)
+__global__ void __launch_bounds__(256)
+k_extract_gradp(const double* __restrict__ xmg, double* __restrict__ p, double* __restrict__ ux,
+                double* __restrict__ uy, double* __restrict__ uz, Level L, int nz, int ny, int nx,
+                int k0, int j0, int i0, double scale)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int j = blockIdx.y * blockDim.y + threadIdx.y;
+    int k = blockIdx.z * blockDim.z + threadIdx.z;
+    if (i >= nx || j >= ny || k >= nz) return;
+    const long long c = ((long long)k * ny + j) * nx + i;
+    const long long m = (long long)(k + k0) * L.sk + (long long)(j + j0) * L.sj + (i + i0);
+    const double p0 = xmg[m] * scale;
+    p[c] = p0;
+    if (i < nx - 1) ux[c] = ux[c] - (xmg[m + 1] * scale - p0);
+    if (j < ny - 1) uy[c] = uy[c] - (xmg[m + L.sj] * scale - p0);
+    if (k < nz - 1) uz[c] = uz[c] - (xmg[m + L.sk] * scale - p0);
+}
+
 // =================================================================================================
 //  box kernels (analytic coefficients): the hot path
 // =================================================================================================
@@ -1247,6 +1286,35 @@ extern "C" int ny_mg_solve_directly(ny_mg* mg, double* p, const double* div, ny_
     TRY(ny_mg_solve(mg, stats, stream));
     ny_prof_scope ps(mg->ctx, NY_PROF_MG_EMBED, st);
     k_extract<<<g.grid, g.block, 0, st>>>(mg->lev[0].x, p, L, e.nz, e.ny, e.nx, lo[0], lo[1], lo[2], scale);
+    LAUNCH_OK(mg);
+    return NY_OK;
+}
+
+// compute_p (core/projection.py:39-87) in three launches around the solve: div from u (U = u*ids2 on
+// the fly) written to `div` and embedded in b, halo fill of b, solve, p = x*scale and u -= delta p.
+extern "C" int ny_mg_project(ny_mg* mg, double* ux, double* uy, double* uz, double* div, double* p,
+                             double idx2, double idy2, double idz2, ny_ext e, const int lo[3], double scale,
+                             ny_mg_stats* stats, void* stream)
+{
+    NY_REQUIRE(mg && ux && uy && uz && div && p && lo, "null argument");
+    Level& L = mg->lev[0];
+    const int nh = mg->nh;
+    NY_REQUIRE(lo[0] + e.nz <= L.nz && lo[1] + e.ny <= L.ny + 2 * nh && lo[2] + e.nx <= L.nx + 2 * nh &&
+               lo[0] >= 0 && lo[1] >= 0 && lo[2] >= 0, "model array does not fit the multigrid array");
+    cudaStream_t st = ny_stream(stream);
+    ny_grid3 g = ny_cells_launch(e.nz, e.ny, e.nx);
+    {
+        ny_prof_scope ps(mg->ctx, NY_PROF_DIV, st);
+        k_div_embed<<<g.grid, g.block, 0, st>>>(ux, uy, uz, div, L.b, idx2, idy2, idz2, L, e.nz, e.ny, e.nx, lo[0], lo[1], lo[2]);
+        LAUNCH_OK(mg);
+    }
+    {   // what halo.fill(div) before the embedding does in the reference (mgfordriver.py:70-72)
+        ny_prof_scope ps(mg->ctx, NY_PROF_HALO, st);
+        TRY(fill(mg, st, L, L.b));
+    }
+    TRY(ny_mg_solve(mg, stats, stream));
+    ny_prof_scope ps(mg->ctx, NY_PROF_GRADP, st);
+    k_extract_gradp<<<g.grid, g.block, 0, st>>>(mg->lev[0].x, p, ux, uy, uz, L, e.nz, e.ny, e.nx, lo[0], lo[1], lo[2], scale);
     LAUNCH_OK(mg);
     return NY_OK;
 }

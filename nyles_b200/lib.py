@@ -87,6 +87,8 @@ _PROTOS = {
     "ny_mg_get_array": ([_P, _I, _I, _P, _P], _I),
     "ny_mg_solve": ([_P, C.POINTER(ny_mg_stats), _P], _I),
     "ny_mg_solve_directly": ([_P, _P, _P, ny_ext, C.POINTER(_I * 3), _D, C.POINTER(ny_mg_stats), _P], _I),
+    "ny_mg_project": ([_P] + [_P] * 5 + [_D, _D, _D, ny_ext, C.POINTER(_I * 3), _D, C.POINTER(ny_mg_stats), _P], _I),
+    "ny_diag_post": ([_P] + [_P] * 10 + [_D, _D, _D, _D, ny_ext, _P], _I),
     "ny_mg_op": ([_P, _I, _I, _P], _I),
 }
 

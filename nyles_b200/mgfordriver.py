@@ -93,6 +93,16 @@ class MG(object):
                                               self.dx ** 2, C.byref(self._stats), lib.stream()))
         self._record()
 
+    def project(self, state, grid):
+        """projection.compute_p fused around the in-place solve (ny_mg_project): div from u, solve,
+        p = x*dx**2, u -= delta p."""
+        u = state.u
+        t = state.p.tensor
+        lib.check(self.L.ny_mg_project(self.mg, lib.ptr(u["i"].tensor), lib.ptr(u["j"].tensor), lib.ptr(u["k"].tensor),
+                                       lib.ptr(state.div.tensor), lib.ptr(t), grid.idx2, grid.idy2, grid.idz2,
+                                       lib.ext(t), C.byref(self.lo), self.dx ** 2, C.byref(self._stats), lib.stream()))
+        self._record()
+
     def solve(self, x, b):
         """Full-array interface: b and x have the padded multigrid shape (mgfordriver.py:101-106)."""
         self.set_array(b, ivar=2)

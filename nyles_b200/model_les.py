@@ -73,6 +73,24 @@ class LES(object):
         if not self.euler:                    # model_les_euler.py:98-99 has these two fills commented out
             self.halo.fill(state.b)
             self.halo.fill(state.u)
+        if self.fused:
+            # same statements as below in three launches around the solve plus one for the diagnostics
+            self.mg.project(state, self.grid)
+            self.halo.fill(state.div)          # keeps the model's div array as the reference leaves it
+            self.halo.fill(state.u)
+            if self.nonlinear:
+                u, U, w = state.u, state.U, state.vor
+                t = u["i"].tensor
+                lib.check(lib.load().ny_diag_post(
+                    lib.context(t.device), lib.ptr(u["i"].tensor), lib.ptr(u["j"].tensor), lib.ptr(u["k"].tensor),
+                    lib.ptr(U["i"].tensor), lib.ptr(U["j"].tensor), lib.ptr(U["k"].tensor),
+                    lib.ptr(w["i"].tensor), lib.ptr(w["j"].tensor), lib.ptr(w["k"].tensor), lib.ptr(state.ke.tensor),
+                    self.grid.idx2, self.grid.idy2, self.grid.idz2, float(self.fparameter), lib.ext(t), lib.stream()))
+                self.halo.fill(state.vor)
+                self.halo.fill(state.ke)
+            else:
+                cov_to_contra.U_from_u(state, self.grid)
+            return
         cov_to_contra.U_from_u(state, self.grid)
         projection.compute_p(self.mg, state, self.grid, self.neighbours)
         self.halo.fill(state.u)
