@@ -53,7 +53,9 @@ enum { NY_MG_X = 1, NY_MG_B = 2, NY_MG_R = 3, NY_MG_Y = 4, NY_MG_DIAG = 5, NY_MG
 
 /* single multigrid operations (core/mgfor/operators.f90:127-244), exposed for parity tests */
 enum { NY_MG_OP_SMOOTH = 1, NY_MG_OP_RESIDUAL = 2, NY_MG_OP_RESTRICTION = 3,
-       NY_MG_OP_PROLONGATION = 4, NY_MG_OP_VCYCLE = 5 };
+       NY_MG_OP_PROLONGATION = 4, NY_MG_OP_VCYCLE = 5,
+       NY_MG_OP_FILL = 6 };  /* halo fill of x and b of a level (mod_halo.f90:200-262); tells the solver
+                                that the periodic / slab halos of level 1 are consistent */
 
 typedef struct ny_mg_stats {          /* MG_Stats, core/mgfor/mg_types.f90:45-48 (+normb, history) */
     int nite;                         /* V-cycles done by the last solve */
@@ -68,6 +70,8 @@ enum { NY_PROF_RHS_TRACER = 0, NY_PROF_RHS_MOMENTUM, NY_PROF_VORT_KE, NY_PROF_DI
        NY_PROF_U_FROM_U, NY_PROF_TIMESCHEME, NY_PROF_MAXSPEED, NY_PROF_HALO,
        NY_PROF_MG_SMOOTH_FINE, NY_PROF_MG_RESIDUAL_FINE, NY_PROF_MG_RESTRICT_FINE,
        NY_PROF_MG_PROLONG_FINE, NY_PROF_MG_NORM, NY_PROF_MG_COARSE, NY_PROF_MG_EMBED,
+       NY_PROF_MG_DOWN_FINE,   /* fused smooth + residual + restriction of level 1 */
+       NY_PROF_MG_UP_FINE,     /* fused prolongation + smooth (+ residual norm) of level 1 */
        NY_PROF_NTAGS };
 
 /* ---- context ---------------------------------------------------------------------- */
@@ -213,6 +217,9 @@ int  ny_mg_is_box(ny_mg*);
 /* on = 0 forces the generic kernels that read the coefficient arrays (one rank only; used by the
  * tests to cross-check the two paths), on = 1 re-verifies and re-enables the box kernels */
 int  ny_mg_set_fast_path(ny_mg*, int on);
+/* on = 0: V-cycles run one box kernel per operator; on = 1 (default): the fused TMA-staged legs
+ * (smooth+residual+restriction, prolongation+smooth[+norm]) wherever a level allows them */
+int  ny_mg_set_fused_legs(ny_mg*, int on);
 /* 1-based index of the first level that is replicated on every rank (1 on a single rank) */
 int  ny_mg_first_gathered_level(ny_mg*);
 /* get_pyshape: shape[0..2] = (nz+2nh, ny+2nh, nx+2nh) of level lev (1-based), numpy order */
@@ -237,6 +244,15 @@ int  ny_mg_project(ny_mg*, double* ux, double* uy, double* uz, double* div, doub
                    double idx2, double idy2, double idz2, ny_ext e, const int lo[3], double scale,
                    ny_mg_stats* stats_host, void* stream);
 int  ny_mg_op(ny_mg*, int op, int lev, void* stream);
+
+/* ---- arithmetic primitives, exposed for the parity tests -------------------------------------
+ * ny_debug_weno5: out[t] = weno5(q0[t], q1[t], q2[t], q3[t], q4[t]) (core/weno.f90:25-54) in the
+ * context's arithmetic mode; q is 5 device arrays of n doubles stored back to back.
+ * ny_debug_div: out[t] = the in-range division of ny_weno.cuh applied to a[t] / b[t]; mismatch_host
+ * receives the number of t for which it differs (bitwise) from the IEEE quotient. */
+int  ny_debug_weno5(ny_ctx*, const double* q, double* out, long long n, void* stream);
+int  ny_debug_div(ny_ctx*, const double* a, const double* b, double* out, long long n,
+                  long long* mismatch_host, void* stream);
 
 #ifdef __cplusplus
 }

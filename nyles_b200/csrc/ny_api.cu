@@ -68,7 +68,7 @@ extern "C" void ny_launch_count_reset(ny_ctx* ctx) { if (ctx) ctx->launches = 0;
 static const char* const g_prof_names[NY_PROF_NTAGS] = {
     "rhs_tracer", "rhs_momentum", "vorticity_ke", "div", "gradp", "U_from_u", "timescheme", "maxspeed",
     "halo", "mg_smooth_fine", "mg_residual_fine", "mg_restrict_fine", "mg_prolong_fine", "mg_norm",
-    "mg_coarse_levels", "mg_embed_extract"};
+    "mg_coarse_levels", "mg_embed_extract", "mg_down_fine", "mg_up_fine"};
 
 extern "C" const char* ny_prof_name(int tag)
 {
@@ -103,5 +103,48 @@ extern "C" int ny_prof_start(ny_ctx* ctx, unsigned long long mask)
     if (r != NY_OK) return r;
     for (int t = 0; t < NY_PROF_NTAGS; t++) { ctx->prof_ms[t] = 0.0; ctx->prof_n[t] = 0; }
     ctx->prof_mask = mask;
+    return NY_OK;
+}
+
+// ---- TMA tensor maps -------------------------------------------------------------------------
+// cuTensorMapEncodeTiled is a driver entry point; it is resolved through the runtime so that the
+// library needs no link-time libcuda (the CPU build box has none) and loads without a GPU.
+#include "ny_tma.cuh"
+
+typedef CUresult (*ny_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                       const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                       CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int ny_tma_encode_3d(CUtensorMap* map, const double* base, int nx, int ny, int nz, int bx, int by, int bz)
+{
+    static ny_encode_tiled_fn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+        if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) {
+            ny_set_error("cuTensorMapEncodeTiled is not available from this driver (%s)", cudaGetErrorString(e));
+            return NY_ERR_CUDA;
+        }
+        encode = reinterpret_cast<ny_encode_tiled_fn>(fn);
+    }
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || (nx & 1) || (bx & 1) || bx > 256 || by > 256 || bz > 256 ||
+        bx < 1 || by < 1 || bz < 1) {
+        ny_set_error("ny_tma_encode_3d: array %p (%d,%d,%d) box (%d,%d,%d) violates the TMA alignment rules",
+                     (const void*)base, nz, ny, nx, bz, by, bx);
+        return NY_ERR_ARG;
+    }
+    const cuuint64_t dims[3] = {(cuuint64_t)nx, (cuuint64_t)ny, (cuuint64_t)nz};
+    const cuuint64_t strides[2] = {(cuuint64_t)nx * 8, (cuuint64_t)nx * (cuuint64_t)ny * 8};
+    const cuuint32_t box[3] = {(cuuint32_t)bx, (cuuint32_t)by, (cuuint32_t)bz};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        ny_set_error("cuTensorMapEncodeTiled failed with CUresult %d for array (%d,%d,%d) box (%d,%d,%d)", (int)r, nz, ny,
+                     nx, bz, by, bx);
+        return NY_ERR_CUDA;
+    }
     return NY_OK;
 }

@@ -25,6 +25,7 @@
 // redundantly on every rank (mirror of mg_setup.f90:275-293 / mod_gluesplit.f90).
 #include "ny_common.cuh"
 #include "ny_comm.cuh"
+#include "ny_tma.cuh"
 
 namespace {
 
@@ -51,9 +52,18 @@ struct Box {
 
 }  // namespace
 
+// TMA tensor maps of a level: plane tiles of x, y (the two smoother buffers, swapped together with the
+// pointers) and b; cx / cy: the coarse tile of x / y as the next finer level sees this level (the
+// whole array, or the window of a gathered level that lies under the rank's slab)
+struct LevelMaps { CUtensorMap x, y, b, cx, cy; int ok; };
+
 struct ny_mg {
     ny_ctx* ctx;
     ny_comm* comm;
+    LevelMaps maps[50];
+    int fused;                             // use the fused V-cycle legs where a level allows them
+    int halo_ok;                           // periodic / slab halos of x and b of level 1 are consistent
+    int ysync;                             // wall-halo cells of y equal those of x on every level
     int nranks, rank;
     int nlevels, nh, topology, maxite;
     int xper, yper, zper;
@@ -661,6 +671,8 @@ k_prolong_box(double* __restrict__ xf, const double* __restrict__ xc, Box g, Box
     }
 }
 
+#include "ny_mg_vleg.cuh"
+
 inline int ew_blocks(long long n)
 {
     long long b = (n + 255) / 256;
@@ -771,6 +783,15 @@ inline int chunk_for(ny_mg* mg, int planes, long long tiles, int min_chunk)
     return chunk;
 }
 
+void swap_xy(ny_mg* mg, int lev)
+{
+    Level& L = mg->lev[lev - 1];
+    LevelMaps& M = mg->maps[lev - 1];
+    double* t = L.x; L.x = L.y; L.y = t;
+    CUtensorMap m = M.x; M.x = M.y; M.y = m;
+    m = M.cx; M.cx = M.cy; M.cy = m;
+}
+
 int smooth(ny_mg* mg, cudaStream_t st, int lev)
 {
     Level& L = mg->lev[lev - 1];
@@ -784,8 +805,9 @@ int smooth(ny_mg* mg, cudaStream_t st, int lev)
             dim3 grid(gx, gy, (L.nz + chunk - 1) / chunk);
             k_smooth2<<<grid, S2_NW * 32, 0, st>>>(L.x, L.b, L.y, box_of(mg, L), omega, cff1, chunk);
             LAUNCH_OK(mg);
-            double* t = L.x; L.x = L.y; L.y = t;
+            swap_xy(mg, lev);
         } else {
+            mg->ysync = 0;                 // sweep 1 writes ring 1 of y
             dim3 b(32, 4, 2);
             k_sweep<<<box_grid(L.nx + 2, L.ny + 2, L.nz - 2 * nh + 2, b), b, 0, st>>>(
                 L.x, L.y, L.b, L.idiag, omega, cff1, L, nh, 0, L.nx + 1, 0, L.ny + 1, nh, L.nz + 1 - nh);
@@ -956,15 +978,122 @@ int norm_r_async(ny_mg* mg, cudaStream_t st)
     return finish_sum(mg, st, nparts, 1);
 }
 
-int vcycle(ny_mg* mg, cudaStream_t st)
+// ---- fused V-cycle legs (ny_mg_vleg.cuh) ---------------------------------------------------------
+// A level runs the fused legs when the analytic box coefficients are valid, its interior is at least
+// as wide as the halo in every direction (so that all three halo rings are plain copies) and -- for
+// level 1, whose x and b come from the caller -- its periodic / slab halos are known to be consistent.
+bool leg_ok(const ny_mg* mg, int lev)
+{
+    if (!mg->box || !mg->fused || lev >= mg->nlevels) return false;
+    const Level& L = mg->lev[lev - 1];
+    if (!mg->maps[lev - 1].ok || !mg->maps[lev].ok) return false;
+    if (L.nx < 4 || L.ny < 4 || L.nz - 2 * NH < 4 || ((L.nz - 2 * NH) & 1)) return false;
+    const bool walls_only = !mg->xper && !mg->yper && !L.zlo && !L.zhi;
+    return lev > 1 || walls_only || mg->halo_ok;
+}
+
+// y must agree with x on the wall halos before a leg writes its result into y and swaps
+int sync_y(ny_mg* mg, cudaStream_t st)
+{
+    if (mg->ysync) return NY_OK;
+    for (int l = 0; l < mg->nlevels; l++)
+        NY_CUDA(cudaMemcpyAsync(mg->lev[l].y, mg->lev[l].x, mg->lev[l].n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    mg->ysync = 1;
+    return NY_OK;
+}
+
+struct LegGeom { dim3 grid; int chunk; int nparts; };
+inline LegGeom leg_geom(ny_mg* mg, const Level& L, int tj, int extra, bool even)
+{
+    LegGeom q;
+    const int gx = (L.nx + VL_TI - 1) / VL_TI, gy = (L.ny + tj - 1) / tj, nzi = L.nz - 2 * NH;
+    const long long tiles = (long long)gx * gy, sms = mg->ctx->num_sms;
+    // chunks of planes: minimise (waves of CTAs) x (planes marched per CTA, including the pipeline fill)
+    int best = 1;
+    long long best_cost = -1;
+    for (int nc = 1; nc <= 64 && nc * 8 <= (nzi > 8 ? nzi : 8); nc++) {
+        int chunk = (nzi + nc - 1) / nc;
+        if (even && (chunk & 1)) chunk++;
+        const int ncc = (nzi + chunk - 1) / chunk;
+        const long long waves = (tiles * ncc + sms - 1) / sms;
+        const long long cost = waves * (chunk + extra);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = chunk; }
+    }
+    q.chunk = best;
+    const int gz = (nzi + best - 1) / best;
+    q.grid = dim3(gx, gy, gz);
+    q.nparts = gx * gy * gz;
+    return q;
+}
+
+template <bool PRO, int POST>
+int launch_leg(ny_mg* mg, cudaStream_t st, int lev, const Level& V)
+{
+    using LY = VlegLayout<PRO, POST>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        NY_CUDA(cudaFuncSetAttribute(k_vleg<PRO, POST>, cudaFuncAttributeMaxDynamicSharedMemorySize, LY::bytes));
+        attr_set = true;
+    }
+    Level& F = mg->lev[lev - 1];
+    LevelMaps& M = mg->maps[lev - 1];
+    const LegGeom q = leg_geom(mg, F, LY::tj, POST != POST_NONE ? 6 : 4, POST == POST_RESTRICT);
+    if (POST == POST_NORM && q.nparts > MAX_PARTIALS) { ny_set_error("too many partial sums"); return NY_ERR_ARG; }
+    const double omega = mg->omega, cff1 = 1.0 - omega;
+    k_vleg<PRO, POST><<<q.grid, VL_NW * 32, LY::bytes, st>>>(M.x, M.b, PRO ? mg->maps[lev].cx : M.x, F.y, V.b, mg->d_red,
+                                                              box_of(mg, F), box_of(mg, V), omega, cff1, q.chunk);
+    LAUNCH_OK(mg);
+    swap_xy(mg, lev);
+    return POST == POST_NORM ? q.nparts : 0;
+}
+
+// smooth(lev); residual(lev); restriction(lev)   (solvers.f90:41-46)
+int down_leg(ny_mg* mg, cudaStream_t st, int lev)
+{
+    Level& F = mg->lev[lev - 1];
+    Level& C = mg->lev[lev];
+    Level V = coarse_view(mg, lev);
+    TRY(sync_y(mg, st));
+    {
+        ny_prof_scope ps(mg->ctx, lev == 1 ? NY_PROF_MG_DOWN_FINE : NY_PROF_MG_COARSE, st);
+        int r = launch_leg<false, POST_RESTRICT>(mg, st, lev, V);
+        if (r < 0) return r;
+        NY_CUDA(cudaMemsetAsync(C.x, 0, C.n * sizeof(double), st));           // operators.f90:209
+    }
+    TRY(fill(mg, st, F, F.x));
+    TRY(gather_after_restriction(mg, st, lev));
+    return fill(mg, st, C, C.b);
+}
+
+// prolongation(lev); smooth(lev)   (solvers.f90:51-54); with_norm: also sum r^2 of the result -> partials
+int up_leg(ny_mg* mg, cudaStream_t st, int lev, bool with_norm, int* nparts)
+{
+    Level& F = mg->lev[lev - 1];
+    Level V = coarse_view(mg, lev);
+    TRY(sync_y(mg, st));
+    {
+        ny_prof_scope ps(mg->ctx, lev == 1 ? NY_PROF_MG_UP_FINE : NY_PROF_MG_COARSE, st);
+        int r = with_norm ? launch_leg<true, POST_NORM>(mg, st, lev, V) : launch_leg<true, POST_NONE>(mg, st, lev, V);
+        if (r < 0) return r;
+        if (nparts) *nparts = r;
+    }
+    return fill(mg, st, F, F.x);
+}
+
+// solvers.f90:35-55.  norm_parts != nullptr: the caller wants sum r^2 of level 1 after the cycle; if the
+// last leg could provide it, *norm_parts = number of partial sums waiting in d_red, else 0.
+int vcycle(ny_mg* mg, cudaStream_t st, int* norm_parts = nullptr)
 {
     const int lev1 = mg->nlevels - 1;
+    if (norm_parts) *norm_parts = 0;
     for (int lev = 1; lev <= lev1; lev++) {
+        if (leg_ok(mg, lev)) { TRY(down_leg(mg, st, lev)); continue; }
         TRY(smooth(mg, st, lev));
         TRY(residual_restriction(mg, st, lev));
     }
     TRY(smooth(mg, st, lev1 + 1));
     for (int lev = lev1; lev >= 1; lev--) {
+        if (leg_ok(mg, lev)) { TRY(up_leg(mg, st, lev, lev == 1 && norm_parts, norm_parts)); continue; }
         TRY(prolongation(mg, st, lev));
         TRY(smooth(mg, st, lev));
     }
@@ -1126,6 +1255,28 @@ int create(ny_ctx* ctx, ny_comm* comm, int nx, int ny, int nz_global, int topolo
             if (need3 > tmp_need) tmp_need = need3;
         }
     }
+    mg->fused = 1;
+    mg->halo_ok = 0;
+    mg->ysync = 1;                                              // x and y are both zero
+    for (int l = 0; l < mg->nlevels; l++) {
+        Level& L = mg->lev[l];
+        LevelMaps& M = mg->maps[l];
+        const int tx = L.nx + 2 * nh, ty = L.ny + 2 * nh;
+        int r = ny_tma_encode_3d(&M.x, L.x, tx, ty, L.nz, VL_RI, VL_RJ, 1);
+        if (r == NY_OK) r = ny_tma_encode_3d(&M.y, L.y, tx, ty, L.nz, VL_RI, VL_RJ, 1);
+        if (r == NY_OK) r = ny_tma_encode_3d(&M.b, L.b, tx, ty, L.nz, VL_RI, VL_RJ, 1);
+        // the coarse tile of this level's x as the finer level sees it
+        int wnz = L.nz;
+        size_t woff = 0;
+        if (l > 0 && !mg->lev[l - 1].gathered && L.gathered) {
+            const int nzc = (mg->lev[l - 1].nz - 2 * nh) / 2;
+            wnz = nzc + 2 * nh;
+            woff = (size_t)rank * nzc * L.sk;
+        }
+        if (r == NY_OK) r = ny_tma_encode_3d(&M.cx, L.x + woff, tx, ty, wnz, VL_CI, VL_CJ, 1);
+        if (r == NY_OK) r = ny_tma_encode_3d(&M.cy, L.y + woff, tx, ty, wnz, VL_CI, VL_CJ, 1);
+        M.ok = r == NY_OK;
+    }
     mg->tmp_doubles = tmp_need;
     if (cudaMalloc(&mg->tmp, tmp_need * sizeof(double)) != cudaSuccess ||
         cudaMalloc(&mg->d_red, (MAX_PARTIALS + 4) * sizeof(double)) != cudaSuccess ||
@@ -1190,8 +1341,16 @@ extern "C" int ny_mg_set_fast_path(ny_mg* mg, int on)
 {
     NY_REQUIRE(mg, "null argument");
     NY_REQUIRE(mg->nranks == 1, "slab multigrids always run the box kernels (they hold no coefficient arrays)");
+    mg->ysync = 0;
     if (on) return verify_box(mg, 0);
     mg->box = 0;
+    return NY_OK;
+}
+
+extern "C" int ny_mg_set_fused_legs(ny_mg* mg, int on)
+{
+    NY_REQUIRE(mg, "null argument");
+    mg->fused = on ? 1 : 0;
     return NY_OK;
 }
 
@@ -1218,6 +1377,8 @@ extern "C" int ny_mg_set_array(ny_mg* mg, int lev, int ivar, const double* src, 
     NY_CUDA(cudaMemcpyAsync(var_ptr(mg, lev, ivar), src, mg->lev[lev - 1].n * sizeof(double),
                             cudaMemcpyDeviceToDevice, ny_stream(stream)));
     if (ivar == NY_MG_MSK) mg->box = 0;          // a user mask: coefficients are no longer those of a box
+    if (ivar == NY_MG_X || ivar == NY_MG_Y) mg->ysync = 0;
+    if (lev == 1 && (ivar == NY_MG_X || ivar == NY_MG_B)) mg->halo_ok = 0;
     return NY_OK;
 }
 
@@ -1253,10 +1414,17 @@ extern "C" int ny_mg_solve(ny_mg* mg, ny_mg_stats* stats, void* stream)
     hist[nres++] = res;
     for (;;) {
         if (res < mg->tol) break;
-        TRY(vcycle(mg, st));
+        int parts = 0;
+        const bool last = nite + 1 >= mg->maxite;            // no residual is evaluated after the last cycle
+        TRY(vcycle(mg, st, last ? nullptr : &parts));
         nite++;
         if (nite >= mg->maxite) break;
-        TRY(norm_r_async(mg, st));
+        if (parts > 0) {                                      // sum r^2 came out of the last leg of the cycle
+            ny_prof_scope ps(mg->ctx, NY_PROF_MG_NORM, st);
+            TRY(finish_sum(mg, st, parts, 1));
+        } else {
+            TRY(norm_r_async(mg, st));
+        }
         TRY(read_scalars(mg, st, 2));
         res = mg->ctx->h_pinned[1] / normb;
         if (nres < 32) hist[nres++] = res;
@@ -1283,6 +1451,8 @@ extern "C" int ny_mg_solve_directly(ny_mg* mg, double* p, const double* div, ny_
         k_embed<<<g.grid, g.block, 0, st>>>(L.b, div, L, e.nz, e.ny, e.nx, lo[0], lo[1], lo[2]);
         LAUNCH_OK(mg);
     }
+    // the caller filled the halo of div (mgfordriver.py:70), x is the halo-filled result of the last solve
+    mg->halo_ok = 1;
     TRY(ny_mg_solve(mg, stats, stream));
     ny_prof_scope ps(mg->ctx, NY_PROF_MG_EMBED, st);
     k_extract<<<g.grid, g.block, 0, st>>>(mg->lev[0].x, p, L, e.nz, e.ny, e.nx, lo[0], lo[1], lo[2], scale);
@@ -1312,6 +1482,7 @@ extern "C" int ny_mg_project(ny_mg* mg, double* ux, double* uy, double* uz, doub
         ny_prof_scope ps(mg->ctx, NY_PROF_HALO, st);
         TRY(fill(mg, st, L, L.b));
     }
+    mg->halo_ok = 1;
     TRY(ny_mg_solve(mg, stats, stream));
     ny_prof_scope ps(mg->ctx, NY_PROF_GRADP, st);
     k_extract_gradp<<<g.grid, g.block, 0, st>>>(mg->lev[0].x, p, ux, uy, uz, L, e.nz, e.ny, e.nx, lo[0], lo[1], lo[2], scale);
@@ -1329,6 +1500,13 @@ extern "C" int ny_mg_op(ny_mg* mg, int op, int lev, void* stream)
     case NY_MG_OP_RESTRICTION: NY_REQUIRE(lev < mg->nlevels, "no coarser level"); return restriction(mg, st, lev, false);
     case NY_MG_OP_PROLONGATION: NY_REQUIRE(lev < mg->nlevels, "no coarser level"); return prolongation(mg, st, lev);
     case NY_MG_OP_VCYCLE: return vcycle(mg, st);
+    case NY_MG_OP_FILL: {
+        Level& L = mg->lev[lev - 1];
+        TRY(fill(mg, st, L, L.x));
+        TRY(fill(mg, st, L, L.b));
+        if (lev == 1) mg->halo_ok = 1;
+        return NY_OK;
+    }
     default: ny_set_error("ny_mg_op: unknown op %d", op); return NY_ERR_ARG;
     }
 }

@@ -201,6 +201,26 @@ k_add_laplacian(const double* __restrict__ phi, double* __restrict__ dphi, doubl
     dphi[c] = acc;
 }
 
+__global__ void __launch_bounds__(256)
+k_debug_weno5(const double* __restrict__ q, double* __restrict__ out, long long n, int fast)
+{
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const double a = q[t], b = q[n + t], c = q[2 * n + t], d = q[3 * n + t], e = q[4 * n + t];
+    out[t] = fast ? nyw::weno5<true>(a, b, c, d, e) : nyw::weno5<false>(a, b, c, d, e);
+}
+
+__global__ void __launch_bounds__(256)
+k_debug_div(const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out, long long n,
+            unsigned long long* __restrict__ mismatch)
+{
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const double q = nyw::div_inrange(a[t], b[t]), ref = a[t] / b[t];
+    out[t] = q;
+    if (__double_as_longlong(q) != __double_as_longlong(ref)) atomicAdd(mismatch, 1ull);
+}
+
 inline bool ext_ok(ny_ext e) { return e.nx >= 5 && e.ny >= 5 && e.nz >= 5; }
 
 }  // namespace
@@ -253,6 +273,28 @@ extern "C" int ny_set_arith(ny_ctx* ctx, int fast)
     return NY_OK;
 }
 extern "C" int ny_get_arith(ny_ctx* ctx) { return ctx ? ctx->fast_arith : 0; }
+
+extern "C" int ny_debug_weno5(ny_ctx* ctx, const double* q, double* out, long long n, void* stream)
+{
+    NY_REQUIRE(ctx && q && out && n > 0, "bad argument");
+    k_debug_weno5<<<(unsigned)((n + 255) / 256), 256, 0, ny_stream(stream)>>>(q, out, n, ctx->fast_arith);
+    NY_CHECK_LAUNCH(ctx);
+    return NY_OK;
+}
+
+extern "C" int ny_debug_div(ny_ctx* ctx, const double* a, const double* b, double* out, long long n,
+                            long long* mismatch_host, void* stream)
+{
+    NY_REQUIRE(ctx && a && b && out && mismatch_host && n > 0, "bad argument");
+    cudaStream_t st = ny_stream(stream);
+    unsigned long long* d_cnt = reinterpret_cast<unsigned long long*>(ctx->d_scratch);
+    NY_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), st));
+    k_debug_div<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, b, out, n, d_cnt);
+    NY_CHECK_LAUNCH(ctx);
+    NY_CUDA(cudaMemcpyAsync(mismatch_host, d_cnt, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    NY_CUDA(cudaStreamSynchronize(st));
+    return NY_OK;
+}
 
 extern "C" int ny_upwind(ny_ctx* ctx, const double* trac, const double* Ux, const double* Uy, const double* Uz,
                          double* dtrac, ny_ext e, void* stream)

@@ -77,6 +77,7 @@ _PROTOS = {
     "ny_mg_set_gather_cells": ([_LL], None),
     "ny_mg_is_box": ([_P], _I),
     "ny_mg_set_fast_path": ([_P, _I], _I),
+    "ny_mg_set_fused_legs": ([_P, _I], _I),
     "ny_mg_first_gathered_level": ([_P], _I),
     "ny_mg_create": ([_P, _I, _I, _I, _I, C.POINTER(_P)], _I),
     "ny_mg_destroy": ([_P], None),
@@ -90,6 +91,8 @@ _PROTOS = {
     "ny_mg_project": ([_P] + [_P] * 5 + [_D, _D, _D, ny_ext, C.POINTER(_I * 3), _D, C.POINTER(ny_mg_stats), _P], _I),
     "ny_diag_post": ([_P] + [_P] * 10 + [_D, _D, _D, _D, ny_ext, _P], _I),
     "ny_mg_op": ([_P, _I, _I, _P], _I),
+    "ny_debug_weno5": ([_P, _P, _P, _LL, _P], _I),
+    "ny_debug_div": ([_P, _P, _P, _P, _LL, C.POINTER(_LL), _P], _I),
 }
 
 EXPORTED = sorted(_PROTOS)
@@ -160,7 +163,7 @@ def launch_count_reset():
         load().ny_launch_count_reset(h)
 
 
-NY_PROF_NTAGS = 16
+NY_PROF_NTAGS = 18
 
 
 def prof_start(mask=(1 << NY_PROF_NTAGS) - 1, device=None):

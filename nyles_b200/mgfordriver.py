@@ -103,9 +103,13 @@ class MG(object):
                                        lib.ext(t), C.byref(self.lo), self.dx ** 2, C.byref(self._stats), lib.stream()))
         self._record()
 
-    def solve(self, x, b):
-        """Full-array interface: b and x have the padded multigrid shape (mgfordriver.py:101-106)."""
+    def solve(self, x, b, fill_halo=False):
+        """Full-array interface: b and x have the padded multigrid shape (mgfordriver.py:101-106).
+        fill_halo: fill the periodic / slab halos of b (and of the warm-start x) first, as
+        solve_directly's caller does; the solver then knows they are consistent."""
         self.set_array(b, ivar=2)
+        if fill_halo:
+            self.op("fill", 1)
         lib.check(self.L.ny_mg_solve(self.mg, C.byref(self._stats), lib.stream()))
         self._record()
         self.get_array(x, ivar=1)
@@ -141,6 +145,10 @@ class MG(object):
         """on=False: generic kernels reading the coefficient arrays; on=True: fused box kernels."""
         lib.check(self.L.ny_mg_set_fast_path(self.mg, 1 if on else 0))
 
+    def set_fused_legs(self, on):
+        """on=False: V-cycles use one box kernel per operator instead of the fused legs."""
+        lib.check(self.L.ny_mg_set_fused_legs(self.mg, 1 if on else 0))
+
     def op(self, name, lev=1):
-        code = dict(smooth=1, residual=2, restriction=3, prolongation=4, vcycle=5)[name]
+        code = dict(smooth=1, residual=2, restriction=3, prolongation=4, vcycle=5, fill=6)[name]
         lib.check(self.L.ny_mg_op(self.mg, code, lev, lib.stream()))

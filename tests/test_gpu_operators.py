@@ -339,3 +339,74 @@ def test_fast_arithmetic_within_north_star_tolerance(K, L, shape):
     L.check(lib.ny_upwind(L.context(), L.ptr(g["b"]), L.ptr(g["Ux"]), L.ptr(g["Uy"]), L.ptr(g["Uz"]), L.ptr(out[0]),
                           L.ext(out[0]), L.stream()))
     assert np.array_equal(ref_db, host(out[0]))
+
+
+def test_in_range_division_is_the_ieee_quotient():
+    """ny_weno.cuh div_inrange (the compiler's fast-path sequence without its range test and slow-path
+    call) against the IEEE quotient, bitwise, over the operand ranges weno5 feeds it: tau5 = 0 or a
+    REAL(4)-representable value down to the float denormals, beta + eps from 1e-16 up, and signed
+    numerators over many decades."""
+    from nyles_b200 import lib
+    L = lib.load()
+    ctx = lib.context()
+    gen = torch.Generator(device="cuda").manual_seed(123)
+    n = 1 << 22
+    total = 0
+    for case in range(6):
+        mant_a = 1.0 + torch.rand(n, dtype=torch.float64, device="cuda", generator=gen)
+        mant_b = 1.0 + torch.rand(n, dtype=torch.float64, device="cuda", generator=gen)
+        ea = torch.randint(-160, 100, (n,), device="cuda", generator=gen).double()
+        eb = torch.randint(-54, 200, (n,), device="cuda", generator=gen).double()
+        a = mant_a * torch.exp2(ea)
+        b = mant_b * torch.exp2(eb)
+        if case == 1:
+            a = a.float().double()                  # REAL(4) values, like tau5
+        if case == 2:
+            a = torch.zeros_like(a)
+        if case == 3:
+            a = -a
+        if case == 4:                               # tau5 next to beta: quotients near 1
+            b = mant_b * torch.exp2(torch.clamp(eb, max=100.0))     # keep the REAL(4) dividend finite
+            a = (b * (1.0 + 1e-3 * torch.randn(n, dtype=torch.float64, device="cuda", generator=gen))).float().double()
+        if case == 5:                               # float denormals as dividend
+            a = (torch.randint(1, 1 << 20, (n,), device="cuda", generator=gen).double() * 2.0 ** -149)
+        out = torch.empty_like(a)
+        bad = C.c_longlong(-1)
+        lib.check(L.ny_debug_div(ctx, lib.ptr(a), lib.ptr(b), lib.ptr(out), n, C.byref(bad), lib.stream()))
+        assert bad.value == 0, "case %d: %d quotients differ from IEEE" % (case, bad.value)
+        assert torch.equal(out, a / b)
+        total += n
+    assert total == 6 * n
+
+
+@pytest.mark.parametrize("fast", [False, True])
+def test_weno5_primitive_against_oracle(fast):
+    """weno5 (core/weno.f90:25-54) on smooth, sharp, still (all-zero, constant) and tiny stencils:
+    strict mode bitwise, fast mode within 1e-13 of the stencil scale."""
+    from nyles_b200 import lib
+    o = Kernels("strict")
+    rng = np.random.default_rng(77)
+    n = 20000
+    q = rng.standard_normal((5, n))
+    q[:, :2000] = 0.0                                        # still fluid
+    q[:, 2000:4000] = 1.0                                    # constant
+    q[:, 4000:6000] *= 1e-12
+    q[:, 6000:8000] = 1.0 + 1e-16 * rng.integers(-3, 4, (5, 2000))   # round-off noise on a constant
+    q[:, 8000:10000] = np.sign(q[:, 8000:10000])            # shocks
+    q[:, 10000:12000] = 1e-7 * rng.standard_normal((5, 2000)) * 1e-16   # vorticity of a potential flow
+    q[:, 12000:14000] *= 1e-150
+    ref = np.array([o.weno5(*q[:, t]) for t in range(n)])
+    L = lib.load()
+    lib.set_arith(fast)
+    try:
+        qd = torch.as_tensor(q, device="cuda").contiguous()
+        out = torch.empty(n, dtype=torch.float64, device="cuda")
+        lib.check(L.ny_debug_weno5(lib.context(), lib.ptr(qd), lib.ptr(out), n, lib.stream()))
+        got = out.cpu().numpy()
+    finally:
+        lib.set_arith(False)
+    if not fast:
+        assert np.array_equal(got, ref)
+    else:
+        scale = np.max(np.abs(q), axis=0) + 1e-300
+        assert np.max(np.abs(got - ref) / scale) <= 1e-13
