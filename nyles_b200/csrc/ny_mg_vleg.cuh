@@ -30,6 +30,7 @@ constexpr int VL_RI = 64;                       // region columns
 constexpr int VL_TI = VL_RI - 6;                // stored columns per tile
 constexpr int VL_S = 4;                         // ring of plane stages (x and b)
 constexpr int VL_SC = 6;                        // ring of coarse planes
+constexpr int VL_L2AHEAD = 6;                   // planes ahead of the one being issued that are prefetched into L2
 constexpr int VL_CJ = VL_NW + 2, VL_CI = 34;    // coarse tile (rows, columns)
 constexpr int VL_PLANE = VL_RJ * VL_RI;         // doubles per plane tile
 constexpr int VL_CBYTES = VL_CJ * VL_CI * 8;    // bytes of one coarse tile
@@ -46,11 +47,160 @@ struct VlegLayout {
     static constexpr int off_z = off_y + 2 * VL_PLANE * 8;
     static constexpr int off_c = off_z + (POST != POST_NONE ? 2 * VL_PLANE * 8 : 0);
     static constexpr int off_misc = off_c + (PRO ? VL_SC * VL_CSLOT : 0);
-    static constexpr int bytes = off_misc + 256;               // recip[8], red[16], full[VL_S]
+    static constexpr int bytes = off_misc + 320;               // recip[8], pcoef[4], red[16], full[VL_S]
 };
 
 __device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
 __device__ __forceinline__ void st2(double* p, double2 v) { *reinterpret_cast<double2*>(p) = v; }
+
+struct P4 { double2 A, B; };           // the 2 x 2 patch of a thread: rows A, B, columns (.x, .y)
+
+// per-thread constants of a leg (live in registers after inlining)
+struct VlegCtx {
+    double *sx, *sb, *sy, *sz;
+    const unsigned char* sc;
+    const double *s_recip, *s_pcoef;
+    double* xo; double* bc;
+    Box g, gc;
+    double omega, cff1;
+    int cA0, cA1, cB0, cB1;            // in-plane neighbour counts (negative: cell outside the domain)
+    double rA0, rA1, rB0, rB1;         // 1 / (count + 2)
+    bool oc0, oc1, orA, orB;           // cell belongs to the stored tile and to the interior
+    int oA, oUp, oDn, oC;              // shared-memory offsets (doubles) inside a plane / coarse tile
+    long long gA;                      // global offset of (row A, column .x) inside a plane
+    int exA0, exA1, exB0, exB1;
+    int ai, ajA;
+    int k0, k1, pb1, pb2, pb3;
+};
+
+// One plane of the pipeline.  FAST: every stage runs, the three planes involved have both k-neighbours
+// inside the domain and the plane written lies in the chunk -- no tests left but the per-cell domain
+// flags.  The roles (minus, centre, plus) of the register sets rotate statically in the caller.
+template <bool PRO, int POST, bool FAST>
+__device__ __forceinline__ void vleg_plane(const VlegCtx& c, int p, int t, const P4& xm, const P4& xc, P4& xp,
+                                           const P4& ym, const P4& yc, P4& yp, const P4& zm, const P4& zc, P4& zp,
+                                           P4& bp, const P4& b1, const P4& b2, double& acc, double& rsum)
+{
+    const Box& g = c.g;
+    double* const px = c.sx + (t & (VL_S - 1)) * VL_PLANE;                          // x[p+1]
+    const int sprev = ((t + VL_S - 1) & (VL_S - 1)) * VL_PLANE;
+    const double* const pxc = c.sx + sprev;                                          // x[p]
+    const double* const pbc = c.sb + sprev;                                          // b[p]
+    const int oA = c.oA, oB = c.oA + VL_RI;
+    xp.A = ld2(px + oA); xp.B = ld2(px + oB);
+    if (PRO) {
+        // x[p+1] += Pcoef * (weights 27 9 9 3 / 9 3 3 1 of the eight nearest coarse cells), basicoperators.f90:173-231
+        const int f = p + 1, kf = f - NH, akc = NH + (kf >> 1), ako = (kf & 1) ? akc + 1 : akc - 1;
+        const double* cb = reinterpret_cast<const double*>(c.sc + (akc % VL_SC) * VL_CSLOT) + c.oC;
+        const double* co = reinterpret_cast<const double*>(c.sc + (ako % VL_SC) * VL_CSLOT) + c.oC;
+        const double b00 = cb[0], b01 = cb[1], b10 = cb[VL_CI], b11 = cb[VL_CI + 1];
+        const double o00 = co[0], o01 = co[1], o10 = co[VL_CI], o11 = co[VL_CI + 1];
+        const int ez = FAST ? 1 : (int)in_z(c.gc, ako);
+        const bool fz = FAST ? true : in_z(g, f);
+        const double pbA0 = 9 * b00 + 3 * b01 + 3 * b10 + b11, poA0 = 9 * o00 + 3 * o01 + 3 * o10 + o11;
+        const double pbA1 = 9 * b01 + 3 * b00 + 3 * b11 + b10, poA1 = 9 * o01 + 3 * o00 + 3 * o11 + o10;
+        const double pbB0 = 9 * b10 + 3 * b11 + 3 * b00 + b01, poB0 = 9 * o10 + 3 * o11 + 3 * o00 + o01;
+        const double pbB1 = 9 * b11 + 3 * b10 + 3 * b01 + b00, poB1 = 9 * o11 + 3 * o10 + 3 * o01 + o00;
+        if (fz && c.cA0 >= 0) xp.A.x = xp.A.x + c.s_pcoef[c.exA0 + ez] * (3 * pbA0 + poA0);
+        if (fz && c.cA1 >= 0) xp.A.y = xp.A.y + c.s_pcoef[c.exA1 + ez] * (3 * pbA1 + poA1);
+        if (fz && c.cB0 >= 0) xp.B.x = xp.B.x + c.s_pcoef[c.exB0 + ez] * (3 * pbB0 + poB0);
+        if (fz && c.cB1 >= 0) xp.B.y = xp.B.y + c.s_pcoef[c.exB1 + ez] * (3 * pbB1 + poB1);
+        st2(px + oA, xp.A);             // the rows above / below read the prolonged plane in the next iteration
+        st2(px + oB, xp.B);
+        nytma::fence_proxy_async();
+    }
+    if (FAST || p >= c.pb1) {           // ---- sweep 1 at plane p (fsmoother3d, basicoperators.f90:363-400)
+        bp.A = ld2(pbc + oA); bp.B = ld2(pbc + oB);
+        const double2 up = ld2(pxc + c.oUp), dn = ld2(pxc + c.oDn);
+        const int cz = FAST ? 2 : cnt_z(g, p);
+        if (cz == 2)
+            sweep_patch(xc.A, xc.B, xm.A, xm.B, xp.A, xp.B, up, dn, bp.A, bp.B, c.rA0, c.rA1, c.rB0, c.rB1,
+                        c.omega, c.cff1, yp.A, yp.B);
+        else                            // planes next to the k ends (CTA-uniform)
+            sweep_patch(xc.A, xc.B, xm.A, xm.B, xp.A, xp.B, up, dn, bp.A, bp.B, c.s_recip[max(c.cA0 + cz, 0)],
+                        c.s_recip[max(c.cA1 + cz, 0)], c.s_recip[max(c.cB0 + cz, 0)], c.s_recip[max(c.cB1 + cz, 0)],
+                        c.omega, c.cff1, yp.A, yp.B);
+        double* const py = c.sy + (p & 1) * VL_PLANE;
+        st2(py + oA, yp.A);
+        st2(py + oB, yp.B);
+    }
+    if (FAST || p >= c.pb2) {           // ---- sweep 2 at plane q = p-1
+        const int q = p - 1;
+        const double* const py = c.sy + (q & 1) * VL_PLANE;
+        const double2 up = ld2(py + c.oUp), dn = ld2(py + c.oDn);
+        const int cz = FAST ? 2 : cnt_z(g, q);
+        if (cz == 2)
+            sweep_patch(yc.A, yc.B, ym.A, ym.B, yp.A, yp.B, up, dn, b1.A, b1.B, c.rA0, c.rA1, c.rB0, c.rB1,
+                        c.omega, c.cff1, zp.A, zp.B);
+        else
+            sweep_patch(yc.A, yc.B, ym.A, ym.B, yp.A, yp.B, up, dn, b1.A, b1.B, c.s_recip[max(c.cA0 + cz, 0)],
+                        c.s_recip[max(c.cA1 + cz, 0)], c.s_recip[max(c.cB0 + cz, 0)], c.s_recip[max(c.cB1 + cz, 0)],
+                        c.omega, c.cff1, zp.A, zp.B);
+        const bool qz = FAST ? true : in_z(g, q);
+        if (!(qz && c.cA0 >= 0)) zp.A.x = xm.A.x;            // outside the domain: x is kept
+        if (!(qz && c.cA1 >= 0)) zp.A.y = xm.A.y;
+        if (!(qz && c.cB0 >= 0)) zp.B.x = xm.B.x;
+        if (!(qz && c.cB1 >= 0)) zp.B.y = xm.B.y;
+        if (POST != POST_NONE) {
+            double* const pz = c.sz + (q & 1) * VL_PLANE;
+            st2(pz + oA, zp.A);
+            st2(pz + oB, zp.B);
+        }
+        if (FAST || (q >= c.k0 && q < c.k1)) {
+            double* const dA = c.xo + (long long)q * g.sk + c.gA;
+            double* const dB = dA + g.sj;
+            if (c.orA) {
+                if (c.oc0 && c.oc1) st2(dA, zp.A);
+                else if (c.oc0) dA[0] = zp.A.x;
+                else if (c.oc1) dA[1] = zp.A.y;
+            }
+            if (c.orB) {
+                if (c.oc0 && c.oc1) st2(dB, zp.B);
+                else if (c.oc0) dB[0] = zp.B.x;
+                else if (c.oc1) dB[1] = zp.B.y;
+            }
+        }
+    }
+    if (POST != POST_NONE && (FAST || p >= c.pb3)) {     // ---- residual at plane q = p-2 (fresidual3d, :300-323)
+        const int q = p - 2;
+        const double* const pz = c.sz + (q & 1) * VL_PLANE;
+        const double2 up = ld2(pz + c.oUp), dn = ld2(pz + c.oDn);
+        const double lA = shfl_up1(zc.A.y), rgA = shfl_dn1(zc.A.x), lB = shfl_up1(zc.B.y), rgB = shfl_dn1(zc.B.x);
+        const double sA0 = lA + zc.A.y + up.x + zc.B.x + zm.A.x + zp.A.x;
+        const double sA1 = zc.A.x + rgA + up.y + zc.B.y + zm.A.y + zp.A.y;
+        const double sB0 = lB + zc.B.y + zc.A.x + dn.x + zm.B.x + zp.B.x;
+        const double sB1 = zc.B.x + rgB + zc.A.y + dn.y + zm.B.y + zp.B.y;
+        const int cz = FAST ? 2 : cnt_z(g, q);
+        const double r0 = b2.A.x + (double)(c.cA0 + cz) * zc.A.x - sA0;
+        const double r1 = b2.A.y + (double)(c.cA1 + cz) * zc.A.y - sA1;
+        const double r2 = b2.B.x + (double)(c.cB0 + cz) * zc.B.x - sB0;
+        const double r3 = b2.B.y + (double)(c.cB1 + cz) * zc.B.y - sB1;
+        if (POST == POST_NORM) {
+            if (FAST || q < c.k1) {     // fnorm, basicoperators.f90:422-440 (interior cells, msk = 1)
+                double a = 0.0;
+                if (c.orA && c.oc0) a = a + r0 * r0;
+                if (c.orA && c.oc1) a = a + r1 * r1;
+                if (c.orB && c.oc0) a = a + r2 * r2;
+                if (c.orB && c.oc1) a = a + r3 * r3;
+                acc = acc + a;
+            }
+        } else {
+            // frestrict_centers3d (:32-60): the coarse cell under columns (e+1, e+2), rows (A, B), planes
+            // (q, q+1); the eight residuals are added in the order of the Fortran loop
+            const double r0n = shfl_dn1(r0), r2n = shfl_dn1(r2);
+            if (FAST || q < c.k1) {
+                if (((q - NH) & 1) == 0) {
+                    rsum = r1 + r0n; rsum = rsum + r3; rsum = rsum + r2n;
+                } else {
+                    rsum = rsum + r1; rsum = rsum + r0n; rsum = rsum + r3; rsum = rsum + r2n;
+                    if (c.orA && c.oc1)
+                        c.bc[(long long)(NH + ((q - 1 - NH) >> 1)) * c.gc.sk + (long long)(NH + ((c.ajA - NH) >> 1)) * c.gc.sj +
+                             (NH + ((c.ai + 1 - NH) >> 1))] = 0.5 * rsum;
+                }
+            }
+        }
+    }
+}
 
 template <bool PRO, int POST>
 __global__ void __launch_bounds__(VL_NW * 32, 1)
@@ -62,20 +212,18 @@ k_vleg(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensor
     constexpr int APT = LY::apron_top, TJ = LY::tj;
     constexpr int NPOST = POST != POST_NONE ? 1 : 0;
     extern __shared__ __align__(1024) unsigned char smem[];
+    double* const s_recip = reinterpret_cast<double*>(smem + LY::off_misc);
+    double* const s_pcoef = s_recip + 8;
+    double* const s_red = s_pcoef + 4;
+    uint64_t* const full = reinterpret_cast<uint64_t*>(s_red + 16);
     double* const sx = reinterpret_cast<double*>(smem + LY::off_x);
     double* const sb = reinterpret_cast<double*>(smem + LY::off_b);
-    double* const sy = reinterpret_cast<double*>(smem + LY::off_y);
-    double* const sz = reinterpret_cast<double*>(smem + LY::off_z);
     unsigned char* const sc = smem + LY::off_c;
-    double* const s_recip = reinterpret_cast<double*>(smem + LY::off_misc);
-    double* const s_red = s_recip + 8;
-    uint64_t* const full = reinterpret_cast<uint64_t*>(s_red + 16);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int e = 2 * lane, rA = 2 * warp;
     const int RX0 = (int)blockIdx.x * VL_TI;                            // array column of region column 0 (even)
     const int RY0 = NH + (int)blockIdx.y * TJ - APT;                    // array row of region row 0
-    const int ai = RX0 + e, ajA = RY0 + rA, ajB = ajA + 1;
     const int k0 = NH + (int)blockIdx.z * kchunk, k1 = min(k0 + kchunk, g.nz - NH);   // stored planes [k0, k1)
     // first iteration that runs sweep 1 / sweep 2 / the residual, first and last iteration, first plane loaded
     const int pb1 = k0 - 1 - NPOST, pb2 = k0 + 1 - NPOST, pb3 = k0 + 2;
@@ -83,6 +231,7 @@ k_vleg(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensor
     const int pl0 = pstart + 1, nplanes = pend - pstart + 1;
 
     if (threadIdx.x < 8) s_recip[threadIdx.x] = threadIdx.x ? 1.0 / (double)threadIdx.x : 0.0;
+    if (threadIdx.x < 4) s_pcoef[threadIdx.x] = pcoef_of(threadIdx.x);
     if (threadIdx.x == 0) {
         for (int s = 0; s < VL_S; s++) nytma::mbar_init(&full[s], 1);
         nytma::fence_barrier_init();
@@ -109,6 +258,11 @@ k_vleg(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensor
             for (; cnext <= mneed; cnext++)
                 nytma::load_3d(sc + (cnext % VL_SC) * VL_CSLOT, &tmc, CX0 & ~1, RY0 / 2 + 1, cnext, &full[s]);
         }
+        // the planes after the next ones are pulled into L2 meanwhile
+        if (t + VL_L2AHEAD < nplanes) {
+            nytma::prefetch_3d(&tmx, RX0, RY0, f + VL_L2AHEAD);
+            nytma::prefetch_3d(&tmb, RX0, RY0, f + VL_L2AHEAD);
+        }
     };
     if (threadIdx.x == 0) {
         nytma::prefetch_map(&tmx);
@@ -119,159 +273,63 @@ k_vleg(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensor
     }
 
     // ---- per-thread constants ------------------------------------------------------------------------
-    // in-plane neighbour counts of the four cells (negative outside the domain), 1/diag for two k-neighbours
-    const int cA0 = cnt_xy(g, ai, ajA), cA1 = cnt_xy(g, ai + 1, ajA), cB0 = cnt_xy(g, ai, ajB), cB1 = cnt_xy(g, ai + 1, ajB);
-    const double rA0 = cA0 >= 0 ? 1.0 / (double)(cA0 + 2) : 0.0, rA1 = cA1 >= 0 ? 1.0 / (double)(cA1 + 2) : 0.0;
-    const double rB0 = cB0 >= 0 ? 1.0 / (double)(cB0 + 2) : 0.0, rB1 = cB1 >= 0 ? 1.0 / (double)(cB1 + 2) : 0.0;
-    // cells of the stored tile that belong to the interior of the array
-    const bool oc0 = e >= 3 && e < 3 + VL_TI && ai < g.nx + NH, oc1 = e + 1 >= 3 && e + 1 < 3 + VL_TI && ai + 1 < g.nx + NH;
-    const bool orA = rA >= APT && rA < APT + TJ && ajA < g.ny + NH, orB = rA + 1 >= APT && rA + 1 < APT + TJ && ajB < g.ny + NH;
-    // shared-memory offsets inside a plane tile
-    const int oA = rA * VL_RI + e, oB = oA + VL_RI;
-    const int oUp = (rA > 0 ? rA - 1 : 0) * VL_RI + e, oDn = (rA + 2 < VL_RJ ? rA + 2 : VL_RJ - 1) * VL_RI + e;
-    const long long gA = (long long)ajA * g.sj + ai, gB = gA + g.sj;
-    // prolongation: coarse tile rows (warp, warp+1) x columns (lane, lane+1); in-domain flags of the
-    // "other" coarse column / row of each fine cell (operators.f90:395-424 for the default mask)
-    int exA0 = 0, exA1 = 0, exB0 = 0, exB1 = 0;
+    VlegCtx c;
+    c.sx = sx; c.sb = sb; c.sc = sc; c.s_recip = s_recip; c.s_pcoef = s_pcoef;
+    c.sy = reinterpret_cast<double*>(smem + LY::off_y);
+    c.sz = reinterpret_cast<double*>(smem + LY::off_z);
+    c.xo = xo; c.bc = bc; c.g = g; c.gc = gc; c.omega = omega; c.cff1 = cff1;
+    c.ai = RX0 + e; c.ajA = RY0 + rA;
+    const int ai = c.ai, ajA = c.ajA, ajB = ajA + 1;
+    c.cA0 = cnt_xy(g, ai, ajA); c.cA1 = cnt_xy(g, ai + 1, ajA); c.cB0 = cnt_xy(g, ai, ajB); c.cB1 = cnt_xy(g, ai + 1, ajB);
+    c.rA0 = c.cA0 >= 0 ? 1.0 / (double)(c.cA0 + 2) : 0.0; c.rA1 = c.cA1 >= 0 ? 1.0 / (double)(c.cA1 + 2) : 0.0;
+    c.rB0 = c.cB0 >= 0 ? 1.0 / (double)(c.cB0 + 2) : 0.0; c.rB1 = c.cB1 >= 0 ? 1.0 / (double)(c.cB1 + 2) : 0.0;
+    c.oc0 = e >= 3 && e < 3 + VL_TI && ai < g.nx + NH; c.oc1 = e + 1 >= 3 && e + 1 < 3 + VL_TI && ai + 1 < g.nx + NH;
+    c.orA = rA >= APT && rA < APT + TJ && ajA < g.ny + NH; c.orB = rA + 1 >= APT && rA + 1 < APT + TJ && ajB < g.ny + NH;
+    c.oA = rA * VL_RI + e;
+    c.oUp = (rA > 0 ? rA - 1 : 0) * VL_RI + e; c.oDn = (rA + 2 < VL_RJ ? rA + 2 : VL_RJ - 1) * VL_RI + e;
+    c.gA = (long long)ajA * g.sj + ai;
+    c.exA0 = c.exA1 = c.exB0 = c.exB1 = 0;
     if (PRO) {
+        // coarse tile rows (warp, warp+1) x columns (lane, lane+1); in-domain flags of the "other" coarse
+        // column / row of each fine cell (operators.f90:395-424 for the default mask)
         const int cx = CX0 + lane, cy = RY0 / 2 + 1 + warp;
         const int x0 = (int)in_x(gc, cx), x1 = (int)in_x(gc, cx + 1), y0 = (int)in_y(gc, cy), y1 = (int)in_y(gc, cy + 1);
-        exA0 = x1 + y1; exA1 = x0 + y1; exB0 = x1 + y0; exB1 = x0 + y0;
+        c.exA0 = x1 + y1; c.exA1 = x0 + y1; c.exB0 = x1 + y0; c.exB1 = x0 + y0;
     }
-    const int oC = warp * VL_CI + lane + (CX0 & 1);
+    c.oC = warp * VL_CI + lane + (CX0 & 1);
+    c.k0 = k0; c.k1 = k1; c.pb1 = pb1; c.pb2 = pb2; c.pb3 = pb3;
+
+    // planes whose two k-neighbours are inside the domain: [zlo1, zhi1]
+    const int zlo1 = g.zlo ? -(1 << 20) : NH + 1, zhi1 = g.zhi ? (1 << 20) : g.nz - NH - 2;
+    // all stages active, planes p-2 .. p (and p+1 and its coarse partner for the prolongation) regular,
+    // stored plane inside the chunk
+    const int fast_lo = max(POST != POST_NONE ? pb3 : pb2, zlo1 + 2), fast_hi = min(k1, zhi1 - (PRO ? 2 : 0));
 
     const double2 zero2 = make_double2(0.0, 0.0);
-    double2 xmA = zero2, xmB = zero2, xcA = zero2, xcB = zero2;
-    double2 ymA = zero2, ymB = zero2, ycA = zero2, ycB = zero2;
-    double2 zmA = zero2, zmB = zero2, zcA = zero2, zcB = zero2;
-    double2 b1A = zero2, b1B = zero2, b2A = zero2, b2B = zero2;
+    P4 X0 = {zero2, zero2}, X1 = X0, X2 = X0, Y0 = X0, Y1 = X0, Y2 = X0, Z0 = X0, Z1 = X0, Z2 = X0, B0 = X0, B1 = X0, B2 = X0;
     double acc = 0.0, rsum = 0.0;
+    int p = pstart;
 
-    auto coef = [&](int cz, double& a0, double& a1, double& b0, double& b1) {
-        if (cz == 2) { a0 = rA0; a1 = rA1; b0 = rB0; b1 = rB1; }
-        else {                                                  // planes next to the k ends (CTA-uniform)
-            a0 = s_recip[max(cA0 + cz, 0)]; a1 = s_recip[max(cA1 + cz, 0)];
-            b0 = s_recip[max(cB0 + cz, 0)]; b1 = s_recip[max(cB1 + cz, 0)];
-        }
-    };
-
-    for (int p = pstart; p <= pend; p++) {
-        const int t = p - pstart;
-        nytma::mbar_wait(&full[t & (VL_S - 1)], (uint32_t)(t / VL_S) & 1u);
-        __syncthreads();                // plane t landed; everything written in the last iteration is visible
-        if (threadIdx.x == 0 && t + 2 < nplanes) issue(t + 2);
-        double* const px = sx + (t & (VL_S - 1)) * VL_PLANE;                       // x[p+1]
-        const double* const pxc = sx + ((t + VL_S - 1) & (VL_S - 1)) * VL_PLANE;   // x[p]
-        const double* const pbc = sb + ((t + VL_S - 1) & (VL_S - 1)) * VL_PLANE;   // b[p]
-        double2 xpA = ld2(px + oA), xpB = ld2(px + oB);
-        if (PRO) {
-            // x[p+1] += Pcoef * (27 9 9 3 / 9 3 3 1 weights of the eight nearest coarse cells), basicoperators.f90:173-231
-            const int f = p + 1, kf = f - NH, akc = NH + (kf >> 1), ako = (kf & 1) ? akc + 1 : akc - 1;
-            const double* cb = reinterpret_cast<const double*>(sc + (akc % VL_SC) * VL_CSLOT) + oC;
-            const double* co = reinterpret_cast<const double*>(sc + (ako % VL_SC) * VL_CSLOT) + oC;
-            const double b00 = cb[0], b01 = cb[1], b10 = cb[VL_CI], b11 = cb[VL_CI + 1];
-            const double o00 = co[0], o01 = co[1], o10 = co[VL_CI], o11 = co[VL_CI + 1];
-            const int ez = (int)in_z(gc, ako);
-            const bool fz = in_z(g, f);
-            const double pbA0 = 9 * b00 + 3 * b01 + 3 * b10 + b11, poA0 = 9 * o00 + 3 * o01 + 3 * o10 + o11;
-            const double pbA1 = 9 * b01 + 3 * b00 + 3 * b11 + b10, poA1 = 9 * o01 + 3 * o00 + 3 * o11 + o10;
-            const double pbB0 = 9 * b10 + 3 * b11 + 3 * b00 + b01, poB0 = 9 * o10 + 3 * o11 + 3 * o00 + o01;
-            const double pbB1 = 9 * b11 + 3 * b10 + 3 * b01 + b00, poB1 = 9 * o11 + 3 * o10 + 3 * o01 + o00;
-            if (fz && cA0 >= 0) xpA.x = xpA.x + pcoef_of(exA0 + ez) * (3 * pbA0 + poA0);
-            if (fz && cA1 >= 0) xpA.y = xpA.y + pcoef_of(exA1 + ez) * (3 * pbA1 + poA1);
-            if (fz && cB0 >= 0) xpB.x = xpB.x + pcoef_of(exB0 + ez) * (3 * pbB0 + poB0);
-            if (fz && cB1 >= 0) xpB.y = xpB.y + pcoef_of(exB1 + ez) * (3 * pbB1 + poB1);
-            st2(px + oA, xpA);          // the rows above / below read the prolonged plane in the next iteration
-            st2(px + oB, xpB);
-            nytma::fence_proxy_async();
-        }
-        double2 ypA = zero2, ypB = zero2, zpA = zero2, zpB = zero2, bpA = zero2, bpB = zero2;
-        if (p >= pb1) {                 // ---- sweep 1 at plane p (fsmoother3d, basicoperators.f90:363-400)
-            bpA = ld2(pbc + oA); bpB = ld2(pbc + oB);
-            double iA0, iA1, iB0, iB1;
-            coef(cnt_z(g, p), iA0, iA1, iB0, iB1);
-            sweep_patch(xcA, xcB, xmA, xmB, xpA, xpB, ld2(pxc + oUp), ld2(pxc + oDn), bpA, bpB,
-                        iA0, iA1, iB0, iB1, omega, cff1, ypA, ypB);
-            double* const py = sy + (p & 1) * VL_PLANE;
-            st2(py + oA, ypA);
-            st2(py + oB, ypB);
-        }
-        if (p >= pb2) {                 // ---- sweep 2 at plane q = p-1
-            const int q = p - 1;
-            const double* const py = sy + (q & 1) * VL_PLANE;
-            double iA0, iA1, iB0, iB1;
-            coef(cnt_z(g, q), iA0, iA1, iB0, iB1);
-            sweep_patch(ycA, ycB, ymA, ymB, ypA, ypB, ld2(py + oUp), ld2(py + oDn), b1A, b1B,
-                        iA0, iA1, iB0, iB1, omega, cff1, zpA, zpB);
-            const bool qz = in_z(g, q);
-            if (!(qz && cA0 >= 0)) zpA.x = xmA.x;            // outside the domain: x is kept
-            if (!(qz && cA1 >= 0)) zpA.y = xmA.y;
-            if (!(qz && cB0 >= 0)) zpB.x = xmB.x;
-            if (!(qz && cB1 >= 0)) zpB.y = xmB.y;
-            if (POST != POST_NONE) {
-                double* const pz = sz + (q & 1) * VL_PLANE;
-                st2(pz + oA, zpA);
-                st2(pz + oB, zpB);
-            }
-            if (q >= k0 && q < k1) {
-                double* const dA = xo + (long long)q * g.sk + gA;
-                double* const dB = xo + (long long)q * g.sk + gB;
-                if (orA) {
-                    if (oc0 && oc1) st2(dA, zpA);
-                    else if (oc0) dA[0] = zpA.x;
-                    else if (oc1) dA[1] = zpA.y;
-                }
-                if (orB) {
-                    if (oc0 && oc1) st2(dB, zpB);
-                    else if (oc0) dB[0] = zpB.x;
-                    else if (oc1) dB[1] = zpB.y;
-                }
-            }
-        }
-        if (POST != POST_NONE && p >= pb3) {     // ---- residual at plane q = p-2 (fresidual3d, :300-323)
-            const int q = p - 2;
-            const double* const pz = sz + (q & 1) * VL_PLANE;
-            const double2 up = ld2(pz + oUp), dn = ld2(pz + oDn);
-            const double lA = shfl_up1(zcA.y), rgA = shfl_dn1(zcA.x), lB = shfl_up1(zcB.y), rgB = shfl_dn1(zcB.x);
-            const double sA0 = lA + zcA.y + up.x + zcB.x + zmA.x + zpA.x;
-            const double sA1 = zcA.x + rgA + up.y + zcB.y + zmA.y + zpA.y;
-            const double sB0 = lB + zcB.y + zcA.x + dn.x + zmB.x + zpB.x;
-            const double sB1 = zcB.x + rgB + zcA.y + dn.y + zmB.y + zpB.y;
-            const int cz = cnt_z(g, q);
-            const double r0 = b2A.x + (double)(cA0 + cz) * zcA.x - sA0;
-            const double r1 = b2A.y + (double)(cA1 + cz) * zcA.y - sA1;
-            const double r2 = b2B.x + (double)(cB0 + cz) * zcB.x - sB0;
-            const double r3 = b2B.y + (double)(cB1 + cz) * zcB.y - sB1;
-            if (POST == POST_NORM) {
-                if (q < k1) {           // fnorm, basicoperators.f90:422-440 (interior cells, msk = 1)
-                    double a = 0.0;
-                    if (orA && oc0) a = a + r0 * r0;
-                    if (orA && oc1) a = a + r1 * r1;
-                    if (orB && oc0) a = a + r2 * r2;
-                    if (orB && oc1) a = a + r3 * r3;
-                    acc = acc + a;
-                }
-            } else {
-                // frestrict_centers3d (:32-60): the coarse cell under columns (e+1, e+2), rows (A, B), planes
-                // (q, q+1); the eight residuals are added in the order of the Fortran loop
-                const double r0n = shfl_dn1(r0), r2n = shfl_dn1(r2);
-                if (q < k1) {
-                    if (((q - NH) & 1) == 0) {
-                        rsum = r1 + r0n; rsum = rsum + r3; rsum = rsum + r2n;
-                    } else {
-                        rsum = rsum + r1; rsum = rsum + r0n; rsum = rsum + r3; rsum = rsum + r2n;
-                        if (orA && oc1)
-                            bc[(long long)(NH + ((q - 1 - NH) >> 1)) * gc.sk + (long long)(NH + ((ajA - NH) >> 1)) * gc.sj +
-                               (NH + ((ai + 1 - NH) >> 1))] = 0.5 * rsum;
-                    }
-                }
-            }
-        }
-        xmA = xcA; xmB = xcB; xcA = xpA; xcB = xpB;
-        ymA = ycA; ymB = ycB; ycA = ypA; ycB = ypB;
-        zmA = zcA; zmB = zcB; zcA = zpA; zcB = zpB;
-        b2A = b1A; b2B = b1B; b1A = bpA; b1B = bpB;
+#define VLEG_STEP(m, c_, n)                                                                                         \
+    {                                                                                                               \
+        if (p > pend) break;                                                                                        \
+        const int t = p - pstart;                                                                                   \
+        nytma::mbar_wait(&full[t & (VL_S - 1)], (uint32_t)(t / VL_S) & 1u);                                         \
+        __syncthreads(); /* plane t landed; everything written in the last iteration is visible */                  \
+        if (threadIdx.x == 0 && t + 2 < nplanes) issue(t + 2);                                                      \
+        if (p >= fast_lo && p <= fast_hi)                                                                           \
+            vleg_plane<PRO, POST, true>(c, p, t, X##m, X##c_, X##n, Y##m, Y##c_, Y##n, Z##m, Z##c_, Z##n, B##n, B##c_, B##m, acc, rsum); \
+        else                                                                                                        \
+            vleg_plane<PRO, POST, false>(c, p, t, X##m, X##c_, X##n, Y##m, Y##c_, Y##n, Z##m, Z##c_, Z##n, B##n, B##c_, B##m, acc, rsum); \
+        p++;                                                                                                        \
     }
+    for (;;) {
+        VLEG_STEP(0, 1, 2)
+        VLEG_STEP(1, 2, 0)
+        VLEG_STEP(2, 0, 1)
+    }
+#undef VLEG_STEP
+
     if (POST == POST_NORM) {
         for (int o = 16; o > 0; o >>= 1) acc = acc + __shfl_xor_sync(0xffffffffu, acc, o);
         if (lane == 0) s_red[warp] = acc;

@@ -63,6 +63,12 @@ __device__ __forceinline__ void load_3d(void* dst, const CUtensorMap* map, int c
         ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
         : "memory");
 }
+// pull the box into L2 only
+__device__ __forceinline__ void prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
 __device__ __forceinline__ void prefetch_map(const CUtensorMap* map)
 {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
