@@ -152,11 +152,22 @@ int ny_rhs(ny_ctx*, const double* b, const double* Ux, const double* Uy, const d
            const double* wx, const double* wy, const double* wz, const double* ke,
            double* db, double* dux, double* duy, double* duz,
            double dz, int flags, ny_ext e, void* stream);
+/* ny_rhs whose momentum kernel applies the time-scheme update of the three velocity components itself
+ * instead of storing du (core/timescheme.py:131-175; u, ub, un = state, stateb, "state copy" arrays of
+ * Timescheme): mode 1 = Euler start-up of LFAM3 (un = ub = u; u += dt du), 2 = LFAM3 predictor,
+ * 3 = LFAM3 corrector (u = un + dt du).  db is still written; the tracer update stays with ny_ts_*. */
+int ny_rhs_update_u(ny_ctx*, const double* b, const double* Ux, const double* Uy, const double* Uz,
+                    const double* wx, const double* wy, const double* wz, const double* ke,
+                    double* db, double* const u[3], double* const ub[3], double* const un[3],
+                    int mode, double dt, double dz, int flags, ny_ext e, void* stream);
 
 /* U_from_u + vorticity + kinenergy (core/model_les.py:112-123) in one pass over u */
 int ny_diag_post(ny_ctx*, const double* ux, const double* uy, const double* uz,
                  double* Ux, double* Uy, double* Uz, double* wx, double* wy, double* wz, double* ke,
                  double idx2, double idy2, double idz2, double fparam, ny_ext e, void* stream);
+/* max(U^2+V^2+W^2) over the whole arrays (core/nyles.py:244-250) as accumulated by the LAST ny_diag_post
+ * of this context, which computes it while it writes U; synchronises the stream.  NaN if any entry is. */
+int ny_diag_post_max_speed2(ny_ctx*, double* out_host, void* stream);
 
 /* ---- time schemes (core/timescheme.py:113-221), n = number of doubles ------------------ */
 int ny_ts_axpy(ny_ctx*, double* s, const double* ds, double a, long long n, void* stream);     /* s += a*ds */

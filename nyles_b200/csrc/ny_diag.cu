@@ -59,16 +59,42 @@ k_kin(const double* __restrict__ ux, const double* __restrict__ uy, const double
     ke[c] = acc;
 }
 
+constexpr unsigned NY_MAX_SLOTS = 4096;   // atomicMax targets of k_diag_post (spread to avoid contention)
+
 // U_from_u + vorticity + kinenergy in one pass over u (same statements as k_scale3, k_vorticity, k_kin)
 __global__ void __launch_bounds__(256)
 k_diag_post(const double* __restrict__ ux, const double* __restrict__ uy, const double* __restrict__ uz,
             double* __restrict__ Ux, double* __restrict__ Uy, double* __restrict__ Uz,
             double* __restrict__ wx, double* __restrict__ wy, double* __restrict__ wz, double* __restrict__ ke,
-            double idx2, double idy2, double idz2, double cx, double cy, double cz, double fparam, Ext e)
+            double idx2, double idy2, double idz2, double cx, double cy, double cz, double fparam, Ext e,
+            unsigned long long* __restrict__ maxbits)
 {
-    CELL_INDEX
-    const double u0 = ux[c], v0 = uy[c], w0 = uz[c];
-    Ux[c] = u0 * idx2; Uy[c] = v0 * idy2; Uz[c] = w0 * idz2;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int j = blockIdx.y * blockDim.y + threadIdx.y;
+    int k = blockIdx.z * blockDim.z + threadIdx.z;
+    const bool inside = i < e.nx && j < e.ny && k < e.nz;
+    // max(U^2+V^2+W^2) of core/nyles.py:244-250 on the fly: non-negative doubles (and +NaN, which then
+    // wins) order like their bit patterns, so an integer atomicMax gives the exact maximum
+    unsigned long long qb = 0ull;
+    const long long c = (long long)k * e.sk + (long long)j * e.sj + i;
+    double u0 = 0.0, v0 = 0.0, w0 = 0.0;
+    if (inside) {
+        u0 = ux[c]; v0 = uy[c]; w0 = uz[c];
+        const double U0 = u0 * idx2, V0 = v0 * idy2, W0 = w0 * idz2;
+        Ux[c] = U0; Uy[c] = V0; Uz[c] = W0;
+        const double q = U0 * U0 + V0 * V0 + W0 * W0;
+        qb = (q == q) ? (unsigned long long)__double_as_longlong(q) : 0x7ff8000000000000ull;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, qb, o);
+        qb = other > qb ? other : qb;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        const unsigned slot = ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8u +
+                              ((threadIdx.z * blockDim.y + threadIdx.y) * blockDim.x + threadIdx.x) / 32u;
+        atomicMax(maxbits + (slot & (NY_MAX_SLOTS - 1)), qb);
+    }
+    if (!inside) return;
     const bool ip = i < e.nx - 1, jp = j < e.ny - 1, kp = k < e.nz - 1;
     if (kp) wx[c] = jp ? uz[c + e.sj] - w0 - uy[c + e.sk] + v0 : 0.0;
     if (ip) wy[c] = kp ? ux[c + e.sk] - u0 - uz[c + 1] + w0 : 0.0;
@@ -180,6 +206,20 @@ k_maxspeed_partial(const double* __restrict__ U, const double* __restrict__ V, c
         partial[blockIdx.x] = r;
     }
 }
+__global__ void __launch_bounds__(256)
+k_maxbits_final(const unsigned long long* __restrict__ bits, double* __restrict__ out)
+{
+    __shared__ unsigned long long sh[256];
+    unsigned long long m = 0ull;
+    for (unsigned t = threadIdx.x; t < NY_MAX_SLOTS; t += blockDim.x) m = bits[t] > m ? bits[t] : m;
+    sh[threadIdx.x] = m;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] = sh[threadIdx.x + o] > sh[threadIdx.x] ? sh[threadIdx.x + o] : sh[threadIdx.x];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = __longlong_as_double((long long)sh[0]);
+}
 __global__ void k_max_final(const double* __restrict__ partial, int nb, double* __restrict__ out)
 {
     double r = partial[0];
@@ -255,10 +295,26 @@ extern "C" int ny_diag_post(ny_ctx* ctx, const double* ux, const double* uy, con
     NY_REQUIRE(ctx && ux && uy && uz && Ux && Uy && Uz && wx && wy && wz && ke, "null argument");
     ny_grid3 g = ny_cells_launch(e.nz, e.ny, e.nx);
     ny_prof_scope ps(ctx, NY_PROF_VORT_KE, ny_stream(stream));
+    NY_REQUIRE(ctx->scratch_doubles >= 32768 + NY_MAX_SLOTS, "scratch too small");
+    unsigned long long* maxbits = reinterpret_cast<unsigned long long*>(ctx->d_scratch + 32768);
+    NY_CUDA(cudaMemsetAsync(maxbits, 0, NY_MAX_SLOTS * sizeof(unsigned long long), ny_stream(stream)));
     k_diag_post<<<g.grid, g.block, 0, ny_stream(stream)>>>(ux, uy, uz, Ux, Uy, Uz, wx, wy, wz, ke, idx2, idy2, idz2,
                                                            (0.5 * idx2) * 0.5, (0.5 * idy2) * 0.5, (0.5 * idz2) * 0.5,
-                                                           fparam, make_ext(e));
+                                                           fparam, make_ext(e), maxbits);
     NY_CHECK_LAUNCH(ctx);
+    return NY_OK;
+}
+
+extern "C" int ny_diag_post_max_speed2(ny_ctx* ctx, double* out_host, void* stream)
+{
+    NY_REQUIRE(ctx && out_host, "null argument");
+    cudaStream_t st = ny_stream(stream);
+    ny_prof_scope ps(ctx, NY_PROF_MAXSPEED, st);
+    k_maxbits_final<<<1, 256, 0, st>>>(reinterpret_cast<unsigned long long*>(ctx->d_scratch + 32768), ctx->d_scratch);
+    NY_CHECK_LAUNCH(ctx);
+    NY_CUDA(cudaMemcpyAsync(ctx->h_pinned, ctx->d_scratch, sizeof(double), cudaMemcpyDeviceToHost, st));
+    NY_CUDA(cudaStreamSynchronize(st));
+    *out_host = ctx->h_pinned[0];
     return NY_OK;
 }
 

@@ -37,8 +37,11 @@ __device__ __forceinline__ double lap_axis(double acc, const double* __restrict_
 //       in a register queue, one new load per plane).
 // DIFF: tracer.py:72-77 interleaves add_laplacian after the upwind pass of each direction.
 constexpr int UP_NW = 8;             // warps (rows) per CTA: UP_NW-1 output rows of 31 cells
+#ifndef UP_MINB
+#define UP_MINB 3
+#endif
 template <bool FAST, bool DIFF>
-__global__ void __launch_bounds__(UP_NW * 32, 3)
+__global__ void __launch_bounds__(UP_NW * 32, UP_MINB)
 k_upwind2(const double* __restrict__ trac, const double* __restrict__ Ux, const double* __restrict__ Uy,
           const double* __restrict__ Uz, double* __restrict__ dtrac, double cx, double cy, double cz, Ext e, int kchunk)
 {
@@ -127,13 +130,36 @@ __device__ __forceinline__ double vf_flux(const double* __restrict__ US, const d
     return nyw::line_flux<FAST>(s, n, u1d, q);
 }
 
+// LFAM3 / Euler-forward update of the three velocity components applied by the momentum kernel itself
+// (core/timescheme.py:131-175; same statements as k_ts in ny_diag.cu): the tendencies never go to memory.
+// mode 0: off (du is stored), 1: Euler start-up, 2: predictor, 3: corrector.  The kernel reads U, vor, ke
+// and b only, so updating u in place is race-free.
+struct TsUpd { int mode; double dt; double *s[3], *sb[3], *sn[3]; };
+
+__device__ __forceinline__ void ts_apply(const TsUpd& u, int comp, long long c, double ds)
+{
+    double* __restrict__ s = u.s[comp];
+    if (u.mode == 2) {                               // timescheme.py:144-162
+        const double v = s[c], vb = u.sb[comp][c];
+        const double lf = vb + (2. * u.dt) * ds;
+        s[c] = (1. / 12.) * (5. * lf + 8. * v - vb);
+        u.sn[comp][c] = v; u.sb[comp][c] = v;
+    } else if (u.mode == 3) {                        // timescheme.py:170-175
+        s[c] = u.sn[comp][c] + u.dt * ds;
+    } else {                                         // timescheme.py:131-139
+        const double v = s[c];
+        u.sn[comp][c] = v; u.sb[comp][c] = v;
+        s[c] = v + u.dt * ds;
+    }
+}
+
 template <bool FAST, bool INTERIOR, bool ACCUM, bool VORTEX, bool BERN>
 __device__ __forceinline__ void momentum_cell(
     const double* __restrict__ Ux, const double* __restrict__ Uy, const double* __restrict__ Uz,
     const double* __restrict__ wx, const double* __restrict__ wy, const double* __restrict__ wz,
     const double* __restrict__ ke, const double* __restrict__ b,
     double* __restrict__ dux, double* __restrict__ duy, double* __restrict__ duz,
-    double cff, int with_b, const Ext& e, int i, int j, int k)
+    double cff, int with_b, const Ext& e, int i, int j, int k, const TsUpd& upd)
 {
     const long long c = (long long)k * e.sk + (long long)j * e.sj + i;
     double ax = ACCUM ? dux[c] : 0.0, ay = ACCUM ? duy[c] : 0.0, az = ACCUM ? duz[c] : 0.0;
@@ -161,16 +187,23 @@ __device__ __forceinline__ void momentum_cell(
             if (with_b) az = az + cff * (b[c + e.sk] + b[c]);         // gradkeandb, :50-51
         }
     }
-    dux[c] = ax; duy[c] = ay; duz[c] = az;
+    if (upd.mode == 0) { dux[c] = ax; duy[c] = ay; duz[c] = az; }
+    else { ts_apply(upd, 0, c, ax); ts_apply(upd, 1, c, ay); ts_apply(upd, 2, c, az); }
 }
 
+// occupancy beats registers here: the kernel waits on loads and on the fp64 division chains, and more
+// resident warps hide both (measured at 512^3, strict arithmetic: 3 CTAs/SM 8.4 ms, 4: 7.1, 5: 6.8, 6: 6.8,
+// 8: 7.0 -- a few spilled registers cost less than the lost warps)
+#ifndef MOM_MINB
+#define MOM_MINB 5
+#endif
 template <bool FAST, bool ACCUM, bool VORTEX, bool BERN>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, MOM_MINB)
 k_momentum(const double* __restrict__ Ux, const double* __restrict__ Uy, const double* __restrict__ Uz,
            const double* __restrict__ wx, const double* __restrict__ wy, const double* __restrict__ wz,
            const double* __restrict__ ke, const double* __restrict__ b,
            double* __restrict__ dux, double* __restrict__ duy, double* __restrict__ duz,
-           double cff, int with_b, Ext e)
+           double cff, int with_b, Ext e, TsUpd upd)
 {
     const int i0 = blockIdx.x * blockDim.x, j0 = blockIdx.y * blockDim.y, k0 = blockIdx.z * blockDim.z;
     const int i = i0 + threadIdx.x, j = j0 + threadIdx.y, k = k0 + threadIdx.z;
@@ -178,11 +211,11 @@ k_momentum(const double* __restrict__ Ux, const double* __restrict__ Uy, const d
     const bool interior = VORTEX && i0 >= 3 && i0 + (int)blockDim.x - 1 <= e.nx - 4 && j0 >= 3 &&
                           j0 + (int)blockDim.y - 1 <= e.ny - 4 && k0 >= 3 && k0 + (int)blockDim.z - 1 <= e.nz - 4;
     if (interior) {
-        momentum_cell<FAST, VORTEX, ACCUM, VORTEX, BERN>(Ux, Uy, Uz, wx, wy, wz, ke, b, dux, duy, duz, cff, with_b, e, i, j, k);
+        momentum_cell<FAST, VORTEX, ACCUM, VORTEX, BERN>(Ux, Uy, Uz, wx, wy, wz, ke, b, dux, duy, duz, cff, with_b, e, i, j, k, upd);
         return;
     }
     if (i >= e.nx || j >= e.ny || k >= e.nz) return;
-    momentum_cell<FAST, false, ACCUM, VORTEX, BERN>(Ux, Uy, Uz, wx, wy, wz, ke, b, dux, duy, duz, cff, with_b, e, i, j, k);
+    momentum_cell<FAST, false, ACCUM, VORTEX, BERN>(Ux, Uy, Uz, wx, wy, wz, ke, b, dux, duy, duz, cff, with_b, e, i, j, k, upd);
 }
 
 __global__ void __launch_bounds__(256)
@@ -252,16 +285,20 @@ static int launch_upwind(ny_ctx* ctx, const double* trac, const double* Ux, cons
 template <bool ACCUM, bool VORTEX, bool BERN>
 static int launch_momentum(ny_ctx* ctx, const double* Ux, const double* Uy, const double* Uz,
                            const double* wx, const double* wy, const double* wz, const double* ke, const double* b,
-                           double* dux, double* duy, double* duz, double cff, int with_b, ny_ext e, cudaStream_t st)
+                           double* dux, double* duy, double* duz, double cff, int with_b, ny_ext e, cudaStream_t st,
+                           const TsUpd* updp = nullptr)
 {
+    TsUpd upd;
+    memset(&upd, 0, sizeof(upd));
+    if (updp) upd = *updp;
     ny_grid3 g = ny_cells_launch(e.nz, e.ny, e.nx);
     ny_prof_scope ps(ctx, NY_PROF_RHS_MOMENTUM, st);
     if (ctx->fast_arith && VORTEX)
         k_momentum<true, ACCUM, VORTEX, BERN><<<g.grid, g.block, 0, st>>>(Ux, Uy, Uz, wx, wy, wz, ke, b, dux, duy, duz,
-                                                                          cff, with_b, make_ext(e));
+                                                                          cff, with_b, make_ext(e), upd);
     else
         k_momentum<false, ACCUM, VORTEX, BERN><<<g.grid, g.block, 0, st>>>(Ux, Uy, Uz, wx, wy, wz, ke, b, dux, duy, duz,
-                                                                           cff, with_b, make_ext(e));
+                                                                           cff, with_b, make_ext(e), upd);
     NY_CHECK_LAUNCH(ctx);
     return NY_OK;
 }
@@ -340,13 +377,13 @@ extern "C" int ny_add_laplacian(ny_ctx* ctx, const double* phi, double* dphi, do
     return NY_OK;
 }
 
-extern "C" int ny_rhs(ny_ctx* ctx, const double* b, const double* Ux, const double* Uy, const double* Uz,
-                      const double* wx, const double* wy, const double* wz, const double* ke,
-                      double* db, double* dux, double* duy, double* duz,
-                      double dz, int flags, ny_ext e, void* stream)
+static int rhs_impl(ny_ctx* ctx, const double* b, const double* Ux, const double* Uy, const double* Uz,
+                    const double* wx, const double* wy, const double* wz, const double* ke,
+                    double* db, double* dux, double* duy, double* duz,
+                    double dz, int flags, ny_ext e, void* stream, const TsUpd* upd)
 {
     const bool euler = flags & 1, linear = flags & 2;
-    NY_REQUIRE(ctx && Ux && Uy && Uz && ke && dux && duy && duz, "null argument");
+    NY_REQUIRE(ctx && Ux && Uy && Uz && ke && (upd || (dux && duy && duz)), "null argument");
     NY_REQUIRE(euler || (b && db), "b and db are required unless the Euler flag is set");
     NY_REQUIRE(linear || (wx && wy && wz), "vorticity is required unless the linear flag is set");
     NY_REQUIRE(ext_ok(e), "every extent must be >= 5 (flux1d closure, core/weno.f90:106-153)");
@@ -357,7 +394,30 @@ extern "C" int ny_rhs(ny_ctx* ctx, const double* b, const double* Ux, const doub
     }
     if (linear)
         return launch_momentum<false, false, true>(ctx, Ux, Uy, Uz, wx, wy, wz, ke, b, dux, duy, duz, 0.5 * dz,
-                                                   euler ? 0 : 1, e, st);
+                                                   euler ? 0 : 1, e, st, upd);
     return launch_momentum<false, true, true>(ctx, Ux, Uy, Uz, wx, wy, wz, ke, b, dux, duy, duz, 0.5 * dz,
-                                              euler ? 0 : 1, e, st);
+                                              euler ? 0 : 1, e, st, upd);
+}
+
+extern "C" int ny_rhs(ny_ctx* ctx, const double* b, const double* Ux, const double* Uy, const double* Uz,
+                      const double* wx, const double* wy, const double* wz, const double* ke,
+                      double* db, double* dux, double* duy, double* duz,
+                      double dz, int flags, ny_ext e, void* stream)
+{
+    return rhs_impl(ctx, b, Ux, Uy, Uz, wx, wy, wz, ke, db, dux, duy, duz, dz, flags, e, stream, nullptr);
+}
+
+extern "C" int ny_rhs_update_u(ny_ctx* ctx, const double* b, const double* Ux, const double* Uy, const double* Uz,
+                               const double* wx, const double* wy, const double* wz, const double* ke,
+                               double* db, double* const u[3], double* const ub[3], double* const un[3],
+                               int mode, double dt, double dz, int flags, ny_ext e, void* stream)
+{
+    NY_REQUIRE(u && ub && un && mode >= 1 && mode <= 3, "bad argument");
+    TsUpd upd;
+    upd.mode = mode; upd.dt = dt;
+    for (int a = 0; a < 3; a++) {
+        NY_REQUIRE(u[a] && un[a] && (mode == 3 || ub[a]), "null field");
+        upd.s[a] = u[a]; upd.sb[a] = ub[a]; upd.sn[a] = un[a];
+    }
+    return rhs_impl(ctx, b, Ux, Uy, Uz, wx, wy, wz, ke, db, nullptr, nullptr, nullptr, dz, flags, e, stream, &upd);
 }

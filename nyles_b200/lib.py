@@ -11,10 +11,11 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnyles_b200.so")
+LIB_PATH = os.environ.get("NYLES_B200_LIB") or os.path.join(_HERE, "libnyles_b200.so")
 
 _lib = None
 _ctx = {}
+u_epoch = 0          # bumped by every library call that writes the contravariant velocity state.U
 
 
 class NylesB200Error(RuntimeError):
@@ -58,6 +59,7 @@ _PROTOS = {
     "ny_U_from_u": ([_P] + [_P] * 6 + [_D, _D, _D, ny_ext, _P], _I),
     "ny_add_laplacian": ([_P, _P, _P, _D, _D, _D, ny_ext, _P], _I),
     "ny_rhs": ([_P] + [_P] * 12 + [_D, _I, ny_ext, _P], _I),
+    "ny_rhs_update_u": ([_P] + [_P] * 9 + [C.POINTER(_P * 3)] * 3 + [_I, _D, _D, _I, ny_ext, _P], _I),
     "ny_ts_axpy": ([_P, _P, _P, _D, _LL, _P], _I),
     "ny_ts_lfam3_first": ([_P, _P, _P, _P, _P, _D, _LL, _P], _I),
     "ny_ts_lfam3_pred": ([_P, _P, _P, _P, _P, _D, _LL, _P], _I),
@@ -91,6 +93,7 @@ _PROTOS = {
     "ny_mg_project": ([_P] + [_P] * 5 + [_D, _D, _D, ny_ext, C.POINTER(_I * 3), _D, C.POINTER(ny_mg_stats), _P], _I),
     "ny_diag_post": ([_P] + [_P] * 10 + [_D, _D, _D, _D, ny_ext, _P], _I),
     "ny_mg_op": ([_P, _I, _I, _P], _I),
+    "ny_diag_post_max_speed2": ([_P, C.POINTER(_D), _P], _I),
     "ny_debug_weno5": ([_P, _P, _P, _LL, _P], _I),
     "ny_debug_div": ([_P, _P, _P, _P, _LL, C.POINTER(_LL), _P], _I),
 }

@@ -46,7 +46,7 @@ class LES(object):
         self.halo = halo.set_halo(param, self.state)
         self.neighbours = param["neighbours"]
         self.timescheme = ts.Timescheme(param, self.state)
-        self.timescheme.set(self.rhs, self.diagnose_var)
+        self.timescheme.set(self.rhs, self.diagnose_var, self.rhs_update_u)
         self.orderA, self.orderVF, self.orderKE = param["orderA"], param["orderVF"], param["orderKE"]
         self.rotating = param["rotating"]
         self.forced = param["forced"]
@@ -66,6 +66,23 @@ class LES(object):
                      npz=param["npz"])
         self.mg.preallocate_for_nyles(grid.dx, param["neighbours"], self.halo)
         self.stats = []
+        self._umax_key = None
+
+    def cached_max_speed2(self):
+        """max(U^2+V^2+W^2) left on the device by the last fused diagnose_var, or None if state.U has been
+        written since (torch-level writes bump the tensors' version counters; the library's own writers of U
+        bump lib.u_epoch)."""
+        key = self._umax_key
+        if key is None:
+            return None
+        state, epoch, versions, ptrs = key
+        U = state.U
+        if state is not self.state or epoch != lib.u_epoch or versions != tuple(U[d].tensor._version for d in "ijk") or \
+                ptrs != tuple(U[d].tensor.data_ptr() for d in "ijk"):
+            return None
+        out = lib.C.c_double()
+        lib.check(lib.load().ny_diag_post_max_speed2(lib.context(U["i"].tensor.device), lib.C.byref(out), lib.stream()))
+        return out.value
 
     # ------------------------------------------------------------------
     @timing
@@ -86,6 +103,10 @@ class LES(object):
                     lib.ptr(U["i"].tensor), lib.ptr(U["j"].tensor), lib.ptr(U["k"].tensor),
                     lib.ptr(w["i"].tensor), lib.ptr(w["j"].tensor), lib.ptr(w["k"].tensor), lib.ptr(state.ke.tensor),
                     self.grid.idx2, self.grid.idy2, self.grid.idz2, float(self.fparameter), lib.ext(t), lib.stream()))
+                # the launch also left max(U^2+V^2+W^2) on the device; valid until U is written again
+                lib.u_epoch += 1
+                self._umax_key = (state, lib.u_epoch, tuple(U[d].tensor._version for d in "ijk"),
+                                  tuple(U[d].tensor.data_ptr() for d in "ijk"))
                 self.halo.fill(state.vor)
                 self.halo.fill(state.ke)
             else:
@@ -138,6 +159,32 @@ class LES(object):
             self.grid.dz, flags, lib.ext(t), lib.stream()))
         if self.euler:
             dstate.b.tensor.zero_()
+
+    def rhs_update_u(self, state, t, dstate, mode, dt, stateb, staten, last=False):
+        """rhs() followed by the time-scheme update of u (mode 1: LFAM3 start-up, 2: predictor, 3: corrector)
+        in one momentum launch; dstate.b is filled as by rhs(), dstate.u is not.  Returns False -- and does
+        nothing -- when something has to see the velocity tendency first (viscosity, forcing)."""
+        if not self.fused or (last and self.add_viscosity) or self.forced:
+            return False
+        U, w = state.U, state.vor
+        t0 = U["i"].tensor
+        flags = (1 if self.euler else 0) | (0 if self.nonlinear else 2)
+
+        def ptr3(vec):
+            return lib.C.byref((lib.C.c_void_p * 3)(*[lib.ptr(vec[d].tensor).value for d in "ijk"]))
+        lib.check(lib.load().ny_rhs_update_u(
+            lib.context(t0.device), lib.ptr(None if self.euler else state.b.tensor),
+            lib.ptr(U["i"].tensor), lib.ptr(U["j"].tensor), lib.ptr(U["k"].tensor),
+            lib.ptr(w["i"].tensor), lib.ptr(w["j"].tensor), lib.ptr(w["k"].tensor), lib.ptr(state.ke.tensor),
+            lib.ptr(None if self.euler else dstate.b.tensor), ptr3(state.u), ptr3(stateb.u), ptr3(staten.u),
+            mode, dt, self.grid.dz, flags, lib.ext(t0), lib.stream()))
+        if self.euler:
+            dstate.b.tensor.zero_()
+        if len(self.traclist) > 1:
+            saved, self.tracer.traclist = self.tracer.traclist, self.traclist[1:]
+            self.tracer.rhstrac(state, dstate)
+            self.tracer.traclist = saved
+        return True
 
     @timing
     def forward(self, t, dt):

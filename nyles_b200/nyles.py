@@ -117,10 +117,13 @@ class Nyles(object):
             return self.dt0
         U = self.model.state.U
         t = U["i"].tensor
-        out = lib.C.c_double()
-        lib.check(lib.load().ny_max_speed2(lib.context(t.device), lib.ptr(U["i"].tensor), lib.ptr(U["j"].tensor),
-                                           lib.ptr(U["k"].tensor), t.numel(), lib.C.byref(out), lib.stream()))
-        U_max = mpitools.global_max(float(np.sqrt(out.value)))
+        umax2 = self.model.cached_max_speed2()            # reduced while diagnose_var wrote U, if still valid
+        if umax2 is None:
+            out = lib.C.c_double()
+            lib.check(lib.load().ny_max_speed2(lib.context(t.device), lib.ptr(U["i"].tensor), lib.ptr(U["j"].tensor),
+                                               lib.ptr(U["k"].tensor), t.numel(), lib.C.byref(out), lib.stream()))
+            umax2 = out.value
+        U_max = mpitools.global_max(float(np.sqrt(umax2)))
         if U_max == 0.0:
             return self.dt_max
         return min(self.cfl / U_max, self.dt_max)

@@ -27,9 +27,25 @@ class Timescheme(object):
             self.ds2 = state.duplicate_prognostic_variables()
         self.L = lib.load()
 
-    def set(self, rhs, diagnose_var):
+    def set(self, rhs, diagnose_var, rhs_update_u=None):
         self.rhs = rhs
         self.diagnose_var = diagnose_var
+        # optional: rhs + update of the velocity components in one launch (model_les.LES.rhs_update_u)
+        self.rhs_update_u = rhs_update_u
+
+    def _rhs_and_update(self, state, t, mode, dt, last, others, fn):
+        """The right-hand side and the update `fn` of every prognostic scalar; the velocity components are
+        updated by the model's fused launch when it offers one."""
+        skip = ()
+        if self.rhs_update_u is not None and \
+                self.rhs_update_u(state, t, self.dstate, mode, dt, self.stateb, self.state, last=last):
+            skip = ("u_i", "u_j", "u_k")
+        else:
+            self.rhs(state, t, self.dstate, last=last)
+        for name in self.prognostic_scalars:
+            if name in skip:
+                continue
+            fn(*([state.get(name).tensor] + [o.get(name).tensor for o in others]))
 
     def _each(self, state, *others):
         for name in self.prognostic_scalars:
@@ -46,22 +62,22 @@ class Timescheme(object):
     # ----------------------------------------
     def LFAM3(self, state, t, dt, **kwargs):
         L = self.L
-        self.rhs(state, t, self.dstate)                              # predictor
+        three = (self.dstate, self.stateb, self.state)
         if self.first:                                               # Euler forward start-up
-            for s, ds, sb, sn in self._each(state, self.dstate, self.stateb, self.state):
-                lib.check(L.ny_ts_lfam3_first(lib.context(s.device), lib.ptr(s), lib.ptr(ds), lib.ptr(sb),
-                                              lib.ptr(sn), dt, s.numel(), lib.stream()))
+            self._rhs_and_update(state, t, 1, dt, False, three, lambda s, ds, sb, sn: lib.check(
+                L.ny_ts_lfam3_first(lib.context(s.device), lib.ptr(s), lib.ptr(ds), lib.ptr(sb), lib.ptr(sn), dt,
+                                    s.numel(), lib.stream())))
             self.first = False
             self.diagnose_var(state)
             return
-        for s, ds, sb, sn in self._each(state, self.dstate, self.stateb, self.state):
-            lib.check(L.ny_ts_lfam3_pred(lib.context(s.device), lib.ptr(s), lib.ptr(ds), lib.ptr(sb),
-                                         lib.ptr(sn), dt, s.numel(), lib.stream()))
+        self._rhs_and_update(state, t, 2, dt, False, three, lambda s, ds, sb, sn: lib.check(     # predictor
+            L.ny_ts_lfam3_pred(lib.context(s.device), lib.ptr(s), lib.ptr(ds), lib.ptr(sb), lib.ptr(sn), dt,
+                               s.numel(), lib.stream())))
         self.diagnose_var(state)
-        self.rhs(state, t + dt * .5, self.dstate, last=True)         # corrector at n+1/2
-        for s, ds, sn in self._each(state, self.dstate, self.state):
-            lib.check(L.ny_ts_lfam3_corr(lib.context(s.device), lib.ptr(s), lib.ptr(ds), lib.ptr(sn), dt,
-                                         s.numel(), lib.stream()))
+        self._rhs_and_update(state, t + dt * .5, 3, dt, True, (self.dstate, self.state),        # corrector at n+1/2
+                             lambda s, ds, sn: lib.check(
+            L.ny_ts_lfam3_corr(lib.context(s.device), lib.ptr(s), lib.ptr(ds), lib.ptr(sn), dt, s.numel(),
+                               lib.stream())))
         self.diagnose_var(state)
 
     # ----------------------------------------
