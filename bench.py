@@ -30,17 +30,33 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+_JSON_OUT = None
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 METRIC = "LES cell-updates/s (fp64, RHS+projection)"
 UNIT = "cell-updates/s"
 
 # ---- workloads ---------------------------------------------------------------
-WEAK_SHAPES = {1: (512, 512, 512), 2: (512, 512, 1024), 4: (512, 1024, 1024), 8: (1024, 1024, 1024)}  # (nx,ny,nz)
+# weak scaling, 512^3 cells per GPU, global (nx, ny, nz).  Default: the near-cubic boxes of SURVEY.md 8(d);
+# the slab interfaces grow from 512^2 to 1024^2 at 8 GPUs.  "weakz": the box grows along z only (constant
+# 512^2 interfaces) -- measured and rejected: mgfor stops coarsening when nx or ny reaches 2, so a 512x512x4096
+# box is left with a 2x2x16 coarsest grid that is only smoothed and the solves run into maxite (39 V-cycles
+# per step instead of 8, 177 ms per step at 8 GPUs).
+WEAK_SHAPES = {1: (512, 512, 512), 2: (512, 512, 1024), 4: (512, 1024, 1024), 8: (1024, 1024, 1024)}
+TALL_SHAPES = {1: (512, 512, 512), 2: (512, 512, 1024), 4: (512, 512, 2048), 8: (512, 512, 4096)}
 
 
 def workload(name, n_gpus):
-    if name == "weak512":          # configs[4] (= configs[2] at N=1): RT instability, closed box, LES
-        nx, ny, nz = WEAK_SHAPES[n_gpus]
-        return dict(name="rayleigh-taylor 512^3 per GPU (weak-scaling sweep), closed, LES, LFAM3",
+    if name in ("weak512", "weakz"):      # configs[4] (= configs[2] at N=1): RT instability, closed box, LES
+        nx, ny, nz = (WEAK_SHAPES if name == "weak512" else TALL_SHAPES)[n_gpus]
+        return dict(name="rayleigh-taylor 512^3 per GPU (weak-scaling sweep%s), closed, LES, LFAM3"
+                         % ("" if name == "weak512" else ", box extended along z"),
                     nx=nx, ny=ny, nz=nz, dx=0.25, geometry="closed", modelname="LES", ic="rt",
                     cfl=0.8, dt_max=0.1)
     if name == "tgv256":           # configs[1]
@@ -135,8 +151,9 @@ def cpu_reference_run(w, steps, warmup):
     """Time `steps` LFAM3 steps of the OpenMP build of the oracle on this host.  Returns
     (cell-updates/s, ms per step, threads, v-cycles per step)."""
     from oracle import model as M
-    threads = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
+    # all host cores (torchrun exports OMP_NUM_THREADS=1 to its workers; the baseline is not a worker)
+    threads = int(os.environ.get("NY_CPU_THREADS", os.cpu_count() or 1))
+    os.environ["OMP_NUM_THREADS"] = str(threads)
     p = M.make_param(nx=w["nx"], ny=w["ny"], nz=w["nz"], geometry=w["geometry"], Lx=w["nx"] * w["dx"],
                      Ly=w["ny"] * w["dx"], Lz=w["nz"] * w["dx"], modelname=w["modelname"], cfl=w["cfl"],
                      dt_max=w["dt_max"])
@@ -191,7 +208,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---- the B200 arm ---------------------------------------------------------------------------
@@ -199,7 +216,9 @@ def run_reference(args):
 def family_bytes_per_cell(euler):
     return {
         "rhs_tracer": 40.0,                       # b, U x3 -> db
-        "rhs_momentum": 80.0 if euler else 88.0,  # U x3, vor x3, ke (, b) -> du x3
+        # U x3, vor x3, ke (, b) read; the launch also applies the time-scheme update of u: predictor reads
+        # u, ub and writes u, un, ub (15 arrays), corrector reads un and writes u (6 arrays): mean per launch
+        "rhs_momentum": (56.0 if euler else 64.0) + 84.0,
         "vorticity_ke": 40.0,                     # vorticity: u x3 -> vor x3 (48); ke: u x3 -> ke (32); mean per group
         "div": 32.0, "gradp": 56.0, "U_from_u": 48.0,
         "timescheme": 36.0,                       # predictor 48, corrector 24 per field; mean per group
@@ -208,9 +227,15 @@ def family_bytes_per_cell(euler):
         "mg_residual_fine": 24.0,                 # x, b -> r
         "mg_restrict_fine": 9.0, "mg_prolong_fine": 17.0, "mg_norm": 8.0,
         "mg_down_fine": 25.0,                     # smooth + residual + restriction fused: x, b -> x, b_coarse
-        "mg_up_fine": 25.0,                       # prolongation + smooth (+ residual norm) fused: x, b, x_coarse -> x
+        "mg_up_fine": 25.0,                       # prolongation + smooth + residual norm fused: x, b, x_coarse -> x
         "mg_embed_extract": 16.0,
     }
+
+
+# fp64 instructions (DADD+DMUL+DFMA+DSETP) per cell in the interior path of the strict kernels, from cuobjdump -sass
+DP_INSTR_PER_CELL = {"rhs_momentum": 693.0, "rhs_tracer": 345.0}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` (profiles/), bytes
+TRAFFIC_NCU = {}
 
 
 def run_ours(args):
@@ -346,9 +371,17 @@ def run_ours(args):
         t_ms, n = timed[top]
         achieved = fam[top] * local_cells / (t_ms / n * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                    "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / peak_gbs, "traffic": TRAFFIC_NCU.get(top), "peak_source": peak_src,
                     "algorithmic_bytes_per_cell": fam[top], "launch_groups": n, "avg_ms": t_ms / n,
                     "share_of_step": t_ms / ms}
+        if top in DP_INSTR_PER_CELL and not args.fast_arith:
+            # the WENO kernels are bound by the fp64 pipe, not by HBM: fp64 instructions per cell counted in
+            # the SASS of the interior path against 64 fp64 lanes per SM per clock
+            rate = DP_INSTR_PER_CELL[top] * local_cells / (t_ms / n * 1e-3)
+            peak_dp = 148 * 64 * 1.965e9
+            roofline["fp64_pipe"] = {"dp_instr_per_cell": DP_INSTR_PER_CELL[top], "achieved_instr_per_s": rate,
+                                     "peak_instr_per_s": peak_dp, "frac": rate / peak_dp,
+                                     "note": "actual limiter of this kernel; the hbm fraction above is low by construction"}
     else:
         roofline = None
     B = bytes_per_cell_step(w, n_vc)
@@ -378,12 +411,17 @@ def run_ours(args):
                        else "strict (source order, no FMA: bit-identical to the reference restatement)"},
             "roofline": roofline, "roofline_step": roofline_step, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": launches, "clocks": clocks}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
+    # the contract is ONE JSON line on stdout; libraries (NCCL's version banner) also write there, so the
+    # real stdout is kept aside for that line and fd 1 points to stderr for everything else
+    global _JSON_OUT
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

@@ -221,6 +221,9 @@ int  ny_mg_create_slab(ny_ctx*, ny_comm* comm, int nx, int ny, int nz_global, in
 /* slab multigrids created afterwards gather every level with at most `cells` global cells
  * (default 64^3); a level whose slab is thinner than 4 planes is gathered in any case */
 void ny_mg_set_gather_cells(long long cells);
+/* slab levels with at least `cells` local cells compute the planes next to their slab neighbours first and
+ * exchange them on a second stream while the rest of the slab is computed (default 2^25) */
+void ny_mg_set_overlap_cells(long long cells);
 void ny_mg_destroy(ny_mg*);
 int  ny_mg_nlevels(ny_mg*);
 /* 1 if the mask is the default box, so that the fused analytic-coefficient kernels are in use */

@@ -104,7 +104,13 @@ extern "C" int ny_comm_init(ny_ctx* ctx, int nranks, int rank, const char* id128
         delete c;
         return NY_ERR_COMM;
     }
-    if (cudaMalloc(&c->d_red, 8 * sizeof(double)) != cudaSuccess) {
+    c->xstream = nullptr; c->ev_ready = nullptr; c->ev_done = nullptr;
+    int lo_prio = 0, hi_prio = 0;
+    cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio);
+    if (cudaStreamCreateWithPriority(&c->xstream, cudaStreamNonBlocking, hi_prio) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming) != cudaSuccess ||
+        cudaMalloc(&c->d_red, 8 * sizeof(double)) != cudaSuccess) {
         ny_set_error("ny_comm_init: cudaMalloc failed");
         g_nccl.CommDestroy(c->nccl);
         delete c;
@@ -119,6 +125,9 @@ extern "C" void ny_comm_free(ny_comm* c)
     if (!c) return;
     if (c->nccl && g_nccl.ok) g_nccl.CommDestroy(c->nccl);
     if (c->d_red) cudaFree(c->d_red);
+    if (c->xstream) cudaStreamDestroy(c->xstream);
+    if (c->ev_ready) cudaEventDestroy(c->ev_ready);
+    if (c->ev_done) cudaEventDestroy(c->ev_done);
     delete c;
 }
 
@@ -156,6 +165,26 @@ int ny_comm_exchange_z(ny_comm* c, double* const* arrays, int nf, size_t plane, 
         if (above >= 0) NY_NCCL(g_nccl.Send(a + (size_t)(lo + nint - nh) * plane, cnt, ncclDouble, above, c->nccl, st));
         if (above >= 0) NY_NCCL(g_nccl.Recv(a + (size_t)(lo + nint) * plane, cnt, ncclDouble, above, c->nccl, st));
         if (below >= 0) NY_NCCL(g_nccl.Recv(a + (size_t)(lo - nh) * plane, cnt, ncclDouble, below, c->nccl, st));
+    }
+    NY_NCCL(g_nccl.GroupEnd());
+    return NY_OK;
+}
+
+int ny_comm_exchange_z2(ny_comm* c, double* a0, size_t plane0, int nint0, double* a1, size_t plane1, int nint1, int nh,
+                        int below, int above, cudaStream_t st)
+{
+    if (!c || (below < 0 && above < 0)) return NY_OK;
+    double* arr[2] = {a0, a1};
+    const size_t plane[2] = {plane0, plane1};
+    const int nint[2] = {nint0, nint1};
+    NY_NCCL(g_nccl.GroupStart());
+    for (int f = 0; f < 2; f++) {                 // same posting order as ny_comm_exchange_z
+        double* a = arr[f];
+        const size_t cnt = (size_t)nh * plane[f];
+        if (below >= 0) NY_NCCL(g_nccl.Send(a + (size_t)nh * plane[f], cnt, ncclDouble, below, c->nccl, st));
+        if (above >= 0) NY_NCCL(g_nccl.Send(a + (size_t)nint[f] * plane[f], cnt, ncclDouble, above, c->nccl, st));
+        if (above >= 0) NY_NCCL(g_nccl.Recv(a + (size_t)(nh + nint[f]) * plane[f], cnt, ncclDouble, above, c->nccl, st));
+        if (below >= 0) NY_NCCL(g_nccl.Recv(a, cnt, ncclDouble, below, c->nccl, st));
     }
     NY_NCCL(g_nccl.GroupEnd());
     return NY_OK;

@@ -10,6 +10,8 @@ struct ny_comm {
     int nranks, rank;
     ncclComm_t nccl;
     double* d_red;            // small device mailbox for host-value reductions
+    cudaStream_t xstream;     // high-priority stream for exchanges that overlap interior kernels
+    cudaEvent_t ev_ready, ev_done;
 };
 
 // all return NY_OK or a negative ny_status; no-ops when c is null or has a single rank
@@ -17,3 +19,7 @@ int ny_comm_allreduce(ny_comm* c, double* d_buf, int n, int op_max, cudaStream_t
 int ny_comm_allgather_inplace(ny_comm* c, double* d_recv, size_t count_per_rank, cudaStream_t st);
 int ny_comm_exchange_z(ny_comm* c, double* const* arrays, int nf, size_t plane, int lo, int nint, int nh,
                        int below, int above, cudaStream_t st);
+// the same for two arrays of different plane sizes / thicknesses in ONE group (a level's x and the next
+// level's b after a fused down leg)
+int ny_comm_exchange_z2(ny_comm* c, double* a0, size_t plane0, int nint0, double* a1, size_t plane1, int nint1, int nh,
+                        int below, int above, cudaStream_t st);

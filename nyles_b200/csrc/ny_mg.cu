@@ -33,6 +33,7 @@ constexpr int MAXLEV = 50;
 constexpr int NH = 3;
 constexpr int MAX_PARTIALS = 1 << 15;
 long long g_gather_cells = 262144;         // levels with at most this many cells are gathered (64^3)
+long long g_overlap_cells = 1LL << 25;     // slab levels with at least this many local cells overlap their halo exchange
 
 struct Level {
     int nx, ny, nz;                        // nz = local planes including the 2*nh halo planes
@@ -762,6 +763,7 @@ int fill(ny_mg* mg, cudaStream_t st, const Level& L, double* a)
     }
     if (dist && (mg->below >= 0 || mg->above >= 0)) {
         double* arr[1] = {a};
+        ny_prof_scope ps(mg->ctx, NY_PROF_HALO, st);
         TRY(ny_comm_exchange_z(mg->comm, arr, 1, (size_t)L.sk, nh, L.nz - 2 * nh, nh, mg->below, mg->above, st));
     }
     return NY_OK;
@@ -875,6 +877,7 @@ int gather_after_restriction(ny_mg* mg, cudaStream_t st, int lev)
     Level& C = mg->lev[lev];
     if (F.gathered || !C.gathered) return NY_OK;
     const size_t cnt = (size_t)((F.nz - 2 * mg->nh) / 2) * C.sk;
+    ny_prof_scope ps(mg->ctx, NY_PROF_HALO, st);
     return ny_comm_allgather_inplace(mg->comm, C.b + (size_t)mg->nh * C.sk, cnt, st);
 }
 
@@ -1003,10 +1006,11 @@ int sync_y(ny_mg* mg, cudaStream_t st)
 }
 
 struct LegGeom { dim3 grid; int chunk; int nparts; };
-inline LegGeom leg_geom(ny_mg* mg, const Level& L, int tj, int extra, bool even)
+// launch geometry for the interior planes [0, nzi) of a level cut into chunks
+inline LegGeom leg_geom(ny_mg* mg, const Level& L, int nzi, int tj, int extra, bool even)
 {
     LegGeom q;
-    const int gx = (L.nx + VL_TI - 1) / VL_TI, gy = (L.ny + tj - 1) / tj, nzi = L.nz - 2 * NH;
+    const int gx = (L.nx + VL_TI - 1) / VL_TI, gy = (L.ny + tj - 1) / tj;
     const long long tiles = (long long)gx * gy, sms = mg->ctx->num_sms;
     // chunks of planes: minimise (waves of CTAs) x (planes marched per CTA, including the pipeline fill)
     int best = 1;
@@ -1026,8 +1030,13 @@ inline LegGeom leg_geom(ny_mg* mg, const Level& L, int tj, int extra, bool even)
     return q;
 }
 
+constexpr int LEG_EDGE = 8;      // planes next to a slab neighbour that are computed first (even, >= 2 * NH)
+
+// One leg of level lev.  On slabs without periodic wraps the planes next to the slab neighbours are
+// computed first; their exchange (x' and, after a down leg, the coarse b) then runs on the communicator's
+// own stream while the rest of the slab is computed.  *exchanged tells the caller that the halos are done.
 template <bool PRO, int POST>
-int launch_leg(ny_mg* mg, cudaStream_t st, int lev, const Level& V)
+int launch_leg(ny_mg* mg, cudaStream_t st, int lev, const Level& V, bool* exchanged)
 {
     using LY = VlegLayout<PRO, POST>;
     static bool attr_set = false;
@@ -1036,15 +1045,55 @@ int launch_leg(ny_mg* mg, cudaStream_t st, int lev, const Level& V)
         attr_set = true;
     }
     Level& F = mg->lev[lev - 1];
+    Level& C = mg->lev[lev];
     LevelMaps& M = mg->maps[lev - 1];
-    const LegGeom q = leg_geom(mg, F, LY::tj, POST != POST_NONE ? 6 : 4, POST == POST_RESTRICT);
-    if (POST == POST_NORM && q.nparts > MAX_PARTIALS) { ny_set_error("too many partial sums"); return NY_ERR_ARG; }
+    const int nzi = F.nz - 2 * NH;
+    const int extra = POST != POST_NONE ? 6 : 4;
     const double omega = mg->omega, cff1 = 1.0 - omega;
-    k_vleg<PRO, POST><<<q.grid, VL_NW * 32, LY::bytes, st>>>(M.x, M.b, PRO ? mg->maps[lev].cx : M.x, F.y, V.b, mg->d_red,
-                                                              box_of(mg, F), box_of(mg, V), omega, cff1, q.chunk);
-    LAUNCH_OK(mg);
+    const Box gf = box_of(mg, F), gv = box_of(mg, V);
+    const CUtensorMap& tmc = PRO ? mg->maps[lev].cx : M.x;
+    int nparts = 0;
+    auto launch = [&](int kz0, int kz1, cudaStream_t s) -> int {
+        const LegGeom q = leg_geom(mg, F, kz1 - kz0, LY::tj, extra, POST == POST_RESTRICT);
+        if (POST == POST_NORM && nparts + q.nparts > MAX_PARTIALS) { ny_set_error("too many partial sums"); return NY_ERR_ARG; }
+        k_vleg<PRO, POST><<<q.grid, VL_NW * 32, LY::bytes, s>>>(M.x, M.b, tmc, F.y, V.b, mg->d_red + nparts, gf, gv, omega,
+                                                                cff1, q.chunk, kz0, kz1);
+        LAUNCH_OK(mg);
+        nparts += q.nparts;
+        return NY_OK;
+    };
+    *exchanged = false;
+    const bool lo = mg->below >= 0, hi = mg->above >= 0;
+    const bool coarse_dist = POST != POST_RESTRICT || !C.gathered;
+    // worth it only where the interior part runs much longer than the exchange (measured: level 1 of a 512^3
+    // slab yes, its 256^3-per-8 coarser levels no)
+    // (and the faces are large: 1024^2 planes gain 3 ms per step at 8 GPUs, 512^2 planes lose 0.5 ms at 2)
+    const bool big = (long long)F.nx * F.ny * nzi >= g_overlap_cells && (long long)F.nx * F.ny * 32 >= g_overlap_cells;
+    if (mg->comm && !F.gathered && (lo || hi) && !mg->xper && !mg->yper && coarse_dist && nzi >= 4 * LEG_EDGE && big) {
+        ny_comm* cm = mg->comm;
+        if (lo) TRY(launch(0, LEG_EDGE, st));
+        if (hi) TRY(launch(nzi - LEG_EDGE, nzi, st));
+        NY_CUDA(cudaEventRecord(cm->ev_ready, st));
+        NY_CUDA(cudaStreamWaitEvent(cm->xstream, cm->ev_ready, 0));
+        {
+            ny_prof_scope ps(mg->ctx, NY_PROF_HALO, cm->xstream);
+            if (POST == POST_RESTRICT)
+                TRY(ny_comm_exchange_z2(cm, F.y, (size_t)F.sk, nzi, C.b, (size_t)C.sk, C.nz - 2 * NH, NH, mg->below, mg->above,
+                                        cm->xstream));
+            else {
+                double* arr[1] = {F.y};
+                TRY(ny_comm_exchange_z(cm, arr, 1, (size_t)F.sk, NH, nzi, NH, mg->below, mg->above, cm->xstream));
+            }
+        }
+        NY_CUDA(cudaEventRecord(cm->ev_done, cm->xstream));
+        TRY(launch(lo ? LEG_EDGE : 0, hi ? nzi - LEG_EDGE : nzi, st));
+        NY_CUDA(cudaStreamWaitEvent(st, cm->ev_done, 0));
+        *exchanged = true;
+    } else {
+        TRY(launch(0, nzi, st));
+    }
     swap_xy(mg, lev);
-    return POST == POST_NORM ? q.nparts : 0;
+    return POST == POST_NORM ? nparts : 0;
 }
 
 // smooth(lev); residual(lev); restriction(lev)   (solvers.f90:41-46)
@@ -1054,11 +1103,20 @@ int down_leg(ny_mg* mg, cudaStream_t st, int lev)
     Level& C = mg->lev[lev];
     Level V = coarse_view(mg, lev);
     TRY(sync_y(mg, st));
+    bool exchanged = false;
     {
         ny_prof_scope ps(mg->ctx, lev == 1 ? NY_PROF_MG_DOWN_FINE : NY_PROF_MG_COARSE, st);
-        int r = launch_leg<false, POST_RESTRICT>(mg, st, lev, V);
-        if (r < 0) return r;
         NY_CUDA(cudaMemsetAsync(C.x, 0, C.n * sizeof(double), st));           // operators.f90:209
+        int r = launch_leg<false, POST_RESTRICT>(mg, st, lev, V, &exchanged);
+        if (r < 0) return r;
+    }
+    if (exchanged) return NY_OK;
+    const bool slabs = mg->below >= 0 || mg->above >= 0;
+    if (slabs && !F.gathered && !C.gathered && !mg->xper && !mg->yper) {
+        // both levels are distributed and there is nothing to wrap locally: one exchange for x and b_coarse
+        ny_prof_scope ps(mg->ctx, NY_PROF_HALO, st);
+        return ny_comm_exchange_z2(mg->comm, F.x, (size_t)F.sk, F.nz - 2 * NH, C.b, (size_t)C.sk, C.nz - 2 * NH, NH,
+                                   mg->below, mg->above, st);
     }
     TRY(fill(mg, st, F, F.x));
     TRY(gather_after_restriction(mg, st, lev));
@@ -1071,12 +1129,15 @@ int up_leg(ny_mg* mg, cudaStream_t st, int lev, bool with_norm, int* nparts)
     Level& F = mg->lev[lev - 1];
     Level V = coarse_view(mg, lev);
     TRY(sync_y(mg, st));
+    bool exchanged = false;
     {
         ny_prof_scope ps(mg->ctx, lev == 1 ? NY_PROF_MG_UP_FINE : NY_PROF_MG_COARSE, st);
-        int r = with_norm ? launch_leg<true, POST_NORM>(mg, st, lev, V) : launch_leg<true, POST_NONE>(mg, st, lev, V);
+        int r = with_norm ? launch_leg<true, POST_NORM>(mg, st, lev, V, &exchanged)
+                          : launch_leg<true, POST_NONE>(mg, st, lev, V, &exchanged);
         if (r < 0) return r;
         if (nparts) *nparts = r;
     }
+    if (exchanged) return NY_OK;
     return fill(mg, st, F, F.x);
 }
 
@@ -1332,6 +1393,7 @@ extern "C" int ny_mg_create_slab(ny_ctx* ctx, ny_comm* comm, int nx, int ny, int
 }
 
 extern "C" void ny_mg_set_gather_cells(long long cells) { g_gather_cells = cells; }
+extern "C" void ny_mg_set_overlap_cells(long long cells) { g_overlap_cells = cells; }
 
 extern "C" int ny_mg_nlevels(ny_mg* mg) { return mg ? mg->nlevels : 0; }
 extern "C" int ny_mg_is_box(ny_mg* mg) { return mg ? mg->box : 0; }

@@ -206,8 +206,9 @@ template <bool PRO, int POST>
 __global__ void __launch_bounds__(VL_NW * 32, 1)
 k_vleg(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmb,
        const __grid_constant__ CUtensorMap tmc, double* __restrict__ xo, double* __restrict__ bc,
-       double* __restrict__ partial, Box g, Box gc, double omega, double cff1, int kchunk)
+       double* __restrict__ partial, Box g, Box gc, double omega, double cff1, int kchunk, int kz0, int kz1)
 {
+    // the launch covers the interior planes [kz0, kz1) (0-based) of the level in chunks of kchunk planes
     using LY = VlegLayout<PRO, POST>;
     constexpr int APT = LY::apron_top, TJ = LY::tj;
     constexpr int NPOST = POST != POST_NONE ? 1 : 0;
@@ -224,7 +225,7 @@ k_vleg(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensor
     const int e = 2 * lane, rA = 2 * warp;
     const int RX0 = (int)blockIdx.x * VL_TI;                            // array column of region column 0 (even)
     const int RY0 = NH + (int)blockIdx.y * TJ - APT;                    // array row of region row 0
-    const int k0 = NH + (int)blockIdx.z * kchunk, k1 = min(k0 + kchunk, g.nz - NH);   // stored planes [k0, k1)
+    const int k0 = NH + kz0 + (int)blockIdx.z * kchunk, k1 = min(k0 + kchunk, NH + kz1);   // stored planes [k0, k1)
     // first iteration that runs sweep 1 / sweep 2 / the residual, first and last iteration, first plane loaded
     const int pb1 = k0 - 1 - NPOST, pb2 = k0 + 1 - NPOST, pb3 = k0 + 2;
     const int pstart = pb1 - 2, pend = k1 + NPOST;

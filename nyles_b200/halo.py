@@ -37,16 +37,18 @@ class Halo(object):
                         (self.above is not None and self.above != self.myrank)
 
     # ------------------------------------------------------------------ public
-    def fill(self, thing):
+    def fill(self, thing, local_only=False):
+        """local_only: wrap the periodic directions of this rank only, no exchange with the slab neighbours
+        (for fields whose halo planes were computed locally from exchanged inputs)."""
         nature = type(thing).__name__
         if nature == "Scalar":
-            self.fillarray(thing.tensor)
+            self.fillarrays([thing.tensor], local_only)
         elif nature == "Vector":
-            self.fillvector(thing)
+            self.fillarrays([thing[d].tensor for d in "ijk"], local_only)
         elif nature == "FieldView":
-            self.fillarray(thing.tensor)
+            self.fillarrays([thing.tensor], local_only)
         elif isinstance(thing, torch.Tensor):
-            self.fillarray(thing)
+            self.fillarrays([thing], local_only)
         else:
             raise ValueError("try to fill halo with unidentified object")
 
@@ -56,7 +58,13 @@ class Halo(object):
     def fillarray(self, x):
         self.fillarrays([x])
 
-    def fillarrays(self, xs):
+    def fillarrays(self, xs, local_only=False):
+        if local_only and self.z_remote:
+            per = (0, 1 if self.yper else 0, 1 if self.xper else 0)
+            if any(per):
+                for x in xs:
+                    self._wrap(x, per)
+            return
         if self.z_remote and xs[0].is_cuda:
             self._exchange_lib(xs)              # z faces through NCCL + local x/y wrap, one library call
             return

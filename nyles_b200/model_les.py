@@ -93,7 +93,12 @@ class LES(object):
         if self.fused:
             # same statements as below in three launches around the solve plus one for the diagnostics
             self.mg.project(state, self.grid)
-            self.halo.fill(state.div)          # keeps the model's div array as the reference leaves it
+            # div, vor and ke are evaluated on every plane of the slab from exchanged u: the planes the RHS
+            # reads (vor: 3 below / 2 above, ke: 1 above) already hold what the neighbour computes, bit for
+            # bit, so only the periodic wraps of this rank are applied; the outermost halo plane of vor / ke
+            # and the z halo of div (never read) are not refreshed from the neighbour
+            lazy = self.halo.z_remote
+            self.halo.fill(state.div, local_only=lazy)   # keeps the model's div array as the reference leaves it
             self.halo.fill(state.u)
             if self.nonlinear:
                 u, U, w = state.u, state.U, state.vor
@@ -107,8 +112,8 @@ class LES(object):
                 lib.u_epoch += 1
                 self._umax_key = (state, lib.u_epoch, tuple(U[d].tensor._version for d in "ijk"),
                                   tuple(U[d].tensor.data_ptr() for d in "ijk"))
-                self.halo.fill(state.vor)
-                self.halo.fill(state.ke)
+                self.halo.fill(state.vor, local_only=lazy)
+                self.halo.fill(state.ke, local_only=lazy)
             else:
                 cov_to_contra.U_from_u(state, self.grid)
             return

@@ -111,6 +111,7 @@ def main():
     torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
     L = lib.load()
     L.ny_mg_set_gather_cells(40000)                 # keep two levels distributed on these small grids
+    L.ny_mg_set_overlap_cells(1 << 18)              # ... and let them take the overlapped-exchange path
 
     # ---------------- phase A: whole problems on one GPU
     ref_models = []
