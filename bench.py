@@ -215,10 +215,12 @@ def run_reference(args):
 # algorithmic bytes per cell of one timed launch group of each kernel family ("Kernels")
 def family_bytes_per_cell(euler):
     return {
-        "rhs_tracer": 40.0,                       # b, U x3 -> db
-        # U x3, vor x3, ke (, b) read; the launch also applies the time-scheme update of u: predictor reads
-        # u, ub and writes u, un, ub (15 arrays), corrector reads un and writes u (6 arrays): mean per launch
-        "rhs_momentum": (56.0 if euler else 64.0) + 84.0,
+        # the RHS launches apply the time-scheme update themselves and write each field once (ny_rhs_step):
+        # tracer: b, U x3 read + the other time level (bb in the predictor, bn in the corrector) -> new b
+        "rhs_tracer": 48.0,
+        # momentum: U x3, vor x3, ke (, b) read; predictor reads u, ub (6 arrays), corrector reads un (3): mean 4.5
+        # arrays per launch; writes the new u (3 arrays)
+        "rhs_momentum": (56.0 if euler else 64.0) + 36.0 + 24.0,
         "vorticity_ke": 40.0,                     # vorticity: u x3 -> vor x3 (48); ke: u x3 -> ke (32); mean per group
         "div": 32.0, "gradp": 56.0, "U_from_u": 48.0,
         "timescheme": 36.0,                       # predictor 48, corrector 24 per field; mean per group
@@ -233,7 +235,7 @@ def family_bytes_per_cell(euler):
 
 
 # fp64 instructions (DADD+DMUL+DFMA+DSETP) per cell in the interior path of the strict kernels, from cuobjdump -sass
-DP_INSTR_PER_CELL = {"rhs_momentum": 693.0, "rhs_tracer": 345.0}
+DP_INSTR_PER_CELL = {"rhs_momentum": 633.0, "rhs_tracer": 321.0}
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` (profiles/), bytes
 TRAFFIC_NCU = {}
 

@@ -161,6 +161,19 @@ int ny_rhs_update_u(ny_ctx*, const double* b, const double* Ux, const double* Uy
                     double* db, double* const u[3], double* const ub[3], double* const un[3],
                     int mode, double dt, double dz, int flags, ny_ext e, void* stream);
 
+/* The right-hand side with the time-scheme update of ALL four prognostic fields applied by the tracer and
+ * momentum kernels themselves (core/timescheme.py:131-175): no tendency array is written.  Field index
+ * 0 = b (ignored with the Euler flag), 1..3 = u components.  The new value of every field goes to out[f],
+ * which must be a separate array: the caller rotates its buffers afterwards --
+ *   mode 1 (Euler start-up) and 2 (LFAM3 predictor): out becomes the state, the old state array IS the
+ *     "state copy" sn (and, for mode 1, is copied to sb);
+ *   mode 3 (LFAM3 corrector, out = sn + dt ds): out becomes the state, sn becomes sb.
+ * Mode 2 reads s and sb, mode 3 reads sn (s is still the array the stencils read), mode 1 reads s. */
+int ny_rhs_step(ny_ctx*, const double* Ux, const double* Uy, const double* Uz,
+                const double* wx, const double* wy, const double* wz, const double* ke,
+                const double* const s[4], const double* const sb[4], const double* const sn[4],
+                double* const out[4], int mode, double dt, double dz, int flags, ny_ext e, void* stream);
+
 /* U_from_u + vorticity + kinenergy (core/model_les.py:112-123) in one pass over u */
 int ny_diag_post(ny_ctx*, const double* ux, const double* uy, const double* uz,
                  double* Ux, double* Uy, double* Uz, double* wx, double* wy, double* wz, double* ke,

@@ -36,6 +36,12 @@ __device__ __forceinline__ double lap_axis(double acc, const double* __restrict_
 //   z : from its own previous plane (the CTA marches along k; the line values q[k-2..k+3] live
 //       in a register queue, one new load per plane).
 // DIFF: tracer.py:72-77 interleaves add_laplacian after the upwind pass of each direction.
+// Time-scheme update of the tracer applied by the kernel itself (same statements as k_ts in ny_diag.cu,
+// core/timescheme.py:131-175).  The kernel reads the tracer with a stencil, so the new value goes to a
+// separate array `out` and the caller rotates its buffers: mode 0: off (dtrac is stored), 1: Euler
+// start-up (out = s + dt ds), 2: LFAM3 predictor (reads sb), 3: LFAM3 corrector (out = sn + dt ds).
+struct TrUpd { int mode; double dt; const double* sb; const double* sn; double* out; };
+
 constexpr int UP_NW = 8;             // warps (rows) per CTA: UP_NW-1 output rows of 31 cells
 #ifndef UP_MINB
 #define UP_MINB 3
@@ -43,7 +49,8 @@ constexpr int UP_NW = 8;             // warps (rows) per CTA: UP_NW-1 output row
 template <bool FAST, bool DIFF>
 __global__ void __launch_bounds__(UP_NW * 32, UP_MINB)
 k_upwind2(const double* __restrict__ trac, const double* __restrict__ Ux, const double* __restrict__ Uy,
-          const double* __restrict__ Uz, double* __restrict__ dtrac, double cx, double cy, double cz, Ext e, int kchunk)
+          const double* __restrict__ Uz, double* __restrict__ dtrac, double cx, double cy, double cz, Ext e, int kchunk,
+          TrUpd upd)
 {
     __shared__ double sFy[2][UP_NW][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -75,6 +82,8 @@ k_upwind2(const double* __restrict__ trac, const double* __restrict__ Ux, const 
         double nux = 0.0, nuy = 0.0, nuz = 0.0, nq = 0.0;
         if (col && k + 1 < k1) { nux = Ux[c + e.sk]; nuy = Uy[c + e.sk]; nuz = Uz[c + e.sk]; }
         if (col && k + 4 < e.nz) nq = trac[c + 4 * e.sk];
+        double told = 0.0;                                            // the other time level the update reads
+        if (upd.mode >= 2 && outp && full) told = upd.mode == 2 ? upd.sb[c] : upd.sn[c];
         double Fx = 0.0, Fy = 0.0, Fz = 0.0;
         if (xy_hot && full && k >= 2 && k <= e.nz - 4) {             // CTA-uniform: branch-free interior path
             Fz = nyw::hot_flux<FAST>(uz, [&](int d) { return zq[d + 2]; });
@@ -101,7 +110,12 @@ k_upwind2(const double* __restrict__ trac, const double* __restrict__ Ux, const 
                 if (DIFF) acc = lap_axis(acc, trac, c, e.sj, j, e.ny, cy);
                 acc = (k == 0) ? acc - Fz : acc + Fz_prev - Fz;
                 if (DIFF) acc = lap_axis(acc, trac, c, e.sk, k, e.nz, cz);
-                dtrac[c] = acc;
+                if (upd.mode == 0) dtrac[c] = acc;
+                else if (upd.mode == 2) {                             // timescheme.py:144-162
+                    const double v = zq[2], lf = told + (2. * upd.dt) * acc;
+                    upd.out[c] = (1. / 12.) * (5. * lf + 8. * v - told);
+                } else if (upd.mode == 3) upd.out[c] = told + upd.dt * acc;      // timescheme.py:170-175
+                else upd.out[c] = zq[2] + upd.dt * acc;               // timescheme.py:131-139
             }
         }
         Fz_prev = Fz;
@@ -120,9 +134,11 @@ template <bool FAST, bool INTERIOR>
 __device__ __forceinline__ double vf_flux(const double* __restrict__ US, const double* __restrict__ W,
                                           long long cs, long long stride, long long tstride, int s, int n)
 {
-    double UU_1 = 0.5 * (US[cs] + US[cs + tstride]);
-    double UU_0 = (INTERIOR || s > 0) ? 0.5 * (US[cs - stride] + US[cs - stride + tstride]) : 0.0;
-    double u1d = 0.5 * (UU_0 + UU_1);                             // fortran_vortex_force.f90:68-72
+    // UU(s) = 0.5*(U + U'), u1d = 0.5*(UU(s-1) + UU(s)) (fortran_vortex_force.f90:68-72): the halvings are
+    // exact, so the two rounded sums added and scaled once give the same bits with two multiplies fewer
+    const double s1 = US[cs] + US[cs + tstride];
+    const double s0 = (INTERIOR || s > 0) ? US[cs - stride] + US[cs - stride + tstride] : 0.0;
+    const double u1d = 0.25 * (s0 + s1);
     auto q = [&](int d) {                                         // q(1)=0, q(k)=vort(k-1), :73-76
         return (INTERIOR || s + d > 0) ? W[cs + (long long)(d - 1) * stride] : 0.0;
     };
@@ -134,11 +150,23 @@ __device__ __forceinline__ double vf_flux(const double* __restrict__ US, const d
 // (core/timescheme.py:131-175; same statements as k_ts in ny_diag.cu): the tendencies never go to memory.
 // mode 0: off (du is stored), 1: Euler start-up, 2: predictor, 3: corrector.  The kernel reads U, vor, ke
 // and b only, so updating u in place is race-free.
-struct TsUpd { int mode; double dt; double *s[3], *sb[3], *sn[3]; };
+// out[] != nullptr: rotating form -- only the new value is written, to out[] (the caller rotates its buffers:
+// the old u array becomes un, see ny_rhs_step); s, sb, sn are then read-only.
+struct TsUpd { int mode; double dt; double *s[3], *sb[3], *sn[3], *out[3]; };
 
 __device__ __forceinline__ void ts_apply(const TsUpd& u, int comp, long long c, double ds)
 {
     double* __restrict__ s = u.s[comp];
+    if (u.out[comp]) {
+        double* __restrict__ o = u.out[comp];
+        if (u.mode == 2) {
+            const double v = s[c], vb = u.sb[comp][c];
+            const double lf = vb + (2. * u.dt) * ds;
+            o[c] = (1. / 12.) * (5. * lf + 8. * v - vb);
+        } else if (u.mode == 3) o[c] = u.sn[comp][c] + u.dt * ds;
+        else o[c] = s[c] + u.dt * ds;
+        return;
+    }
     if (u.mode == 2) {                               // timescheme.py:144-162
         const double v = s[c], vb = u.sb[comp][c];
         const double lf = vb + (2. * u.dt) * ds;
@@ -260,8 +288,12 @@ inline bool ext_ok(ny_ext e) { return e.nx >= 5 && e.ny >= 5 && e.nz >= 5; }
 
 // launch helpers ----------------------------------------------------------------------------------
 static int launch_upwind(ny_ctx* ctx, const double* trac, const double* Ux, const double* Uy, const double* Uz,
-                         double* dtrac, bool diff, double cx, double cy, double cz, ny_ext e, cudaStream_t st)
+                         double* dtrac, bool diff, double cx, double cy, double cz, ny_ext e, cudaStream_t st,
+                         const TrUpd* updp = nullptr)
 {
+    TrUpd upd;
+    memset(&upd, 0, sizeof(upd));
+    if (updp) upd = *updp;
     const int gx = (e.nx + 30) / 31, gy = (e.ny + UP_NW - 2) / (UP_NW - 1);
     // split k so that the launch has ~32 CTAs per SM; each chunk pays one extra plane of z fluxes
     long long want = ((long long)ctx->num_sms * 32 + (long long)gx * gy - 1) / ((long long)gx * gy);
@@ -272,11 +304,11 @@ static int launch_upwind(ny_ctx* ctx, const double* trac, const double* Ux, cons
     Ext x = make_ext(e);
     ny_prof_scope ps(ctx, NY_PROF_RHS_TRACER, st);
     if (ctx->fast_arith) {
-        if (diff) k_upwind2<true, true><<<grid, UP_NW * 32, 0, st>>>(trac, Ux, Uy, Uz, dtrac, cx, cy, cz, x, kchunk);
-        else k_upwind2<true, false><<<grid, UP_NW * 32, 0, st>>>(trac, Ux, Uy, Uz, dtrac, cx, cy, cz, x, kchunk);
+        if (diff) k_upwind2<true, true><<<grid, UP_NW * 32, 0, st>>>(trac, Ux, Uy, Uz, dtrac, cx, cy, cz, x, kchunk, upd);
+        else k_upwind2<true, false><<<grid, UP_NW * 32, 0, st>>>(trac, Ux, Uy, Uz, dtrac, cx, cy, cz, x, kchunk, upd);
     } else {
-        if (diff) k_upwind2<false, true><<<grid, UP_NW * 32, 0, st>>>(trac, Ux, Uy, Uz, dtrac, cx, cy, cz, x, kchunk);
-        else k_upwind2<false, false><<<grid, UP_NW * 32, 0, st>>>(trac, Ux, Uy, Uz, dtrac, cx, cy, cz, x, kchunk);
+        if (diff) k_upwind2<false, true><<<grid, UP_NW * 32, 0, st>>>(trac, Ux, Uy, Uz, dtrac, cx, cy, cz, x, kchunk, upd);
+        else k_upwind2<false, false><<<grid, UP_NW * 32, 0, st>>>(trac, Ux, Uy, Uz, dtrac, cx, cy, cz, x, kchunk, upd);
     }
     NY_CHECK_LAUNCH(ctx);
     return NY_OK;
@@ -380,16 +412,16 @@ extern "C" int ny_add_laplacian(ny_ctx* ctx, const double* phi, double* dphi, do
 static int rhs_impl(ny_ctx* ctx, const double* b, const double* Ux, const double* Uy, const double* Uz,
                     const double* wx, const double* wy, const double* wz, const double* ke,
                     double* db, double* dux, double* duy, double* duz,
-                    double dz, int flags, ny_ext e, void* stream, const TsUpd* upd)
+                    double dz, int flags, ny_ext e, void* stream, const TsUpd* upd, const TrUpd* tupd = nullptr)
 {
     const bool euler = flags & 1, linear = flags & 2;
     NY_REQUIRE(ctx && Ux && Uy && Uz && ke && (upd || (dux && duy && duz)), "null argument");
-    NY_REQUIRE(euler || (b && db), "b and db are required unless the Euler flag is set");
+    NY_REQUIRE(euler || (b && (db || tupd)), "b and db are required unless the Euler flag is set");
     NY_REQUIRE(linear || (wx && wy && wz), "vorticity is required unless the linear flag is set");
     NY_REQUIRE(ext_ok(e), "every extent must be >= 5 (flux1d closure, core/weno.f90:106-153)");
     cudaStream_t st = ny_stream(stream);
     if (!euler) {
-        int r = launch_upwind(ctx, b, Ux, Uy, Uz, db, false, 0.0, 0.0, 0.0, e, st);
+        int r = launch_upwind(ctx, b, Ux, Uy, Uz, db, false, 0.0, 0.0, 0.0, e, st, tupd);
         if (r != NY_OK) return r;
     }
     if (linear)
@@ -414,10 +446,38 @@ extern "C" int ny_rhs_update_u(ny_ctx* ctx, const double* b, const double* Ux, c
 {
     NY_REQUIRE(u && ub && un && mode >= 1 && mode <= 3, "bad argument");
     TsUpd upd;
+    memset(&upd, 0, sizeof(upd));
     upd.mode = mode; upd.dt = dt;
     for (int a = 0; a < 3; a++) {
         NY_REQUIRE(u[a] && un[a] && (mode == 3 || ub[a]), "null field");
         upd.s[a] = u[a]; upd.sb[a] = ub[a]; upd.sn[a] = un[a];
     }
     return rhs_impl(ctx, b, Ux, Uy, Uz, wx, wy, wz, ke, db, nullptr, nullptr, nullptr, dz, flags, e, stream, &upd);
+}
+
+// Fields in s / sb / sn / out: 0 = b (ignored when the Euler flag is set), 1..3 = u components.
+extern "C" int ny_rhs_step(ny_ctx* ctx, const double* Ux, const double* Uy, const double* Uz,
+                           const double* wx, const double* wy, const double* wz, const double* ke,
+                           const double* const s[4], const double* const sb[4], const double* const sn[4],
+                           double* const out[4], int mode, double dt, double dz, int flags, ny_ext e, void* stream)
+{
+    NY_REQUIRE(s && sb && sn && out && mode >= 1 && mode <= 3, "bad argument");
+    const bool euler = flags & 1;
+    TsUpd upd;
+    memset(&upd, 0, sizeof(upd));
+    upd.mode = mode; upd.dt = dt;
+    for (int f = euler ? 1 : 0; f < 4; f++) {
+        NY_REQUIRE(out[f] && s[f] && (mode != 3 || sn[f]) && (mode != 2 || sb[f]), "null field");
+        NY_REQUIRE(out[f] != s[f] && (mode != 3 || out[f] != sn[f]) && (mode != 2 || out[f] != sb[f]),
+                   "out must not be an array the launch reads (the caller rotates its buffers)");
+    }
+    for (int a = 0; a < 3; a++) {
+        upd.s[a] = const_cast<double*>(s[a + 1]); upd.sb[a] = const_cast<double*>(sb[a + 1]);
+        upd.sn[a] = const_cast<double*>(sn[a + 1]); upd.out[a] = out[a + 1];
+    }
+    TrUpd tupd;
+    memset(&tupd, 0, sizeof(tupd));
+    if (!euler) { tupd.mode = mode; tupd.dt = dt; tupd.sb = sb[0]; tupd.sn = sn[0]; tupd.out = out[0]; }
+    return rhs_impl(ctx, euler ? nullptr : s[0], Ux, Uy, Uz, wx, wy, wz, ke, nullptr, nullptr, nullptr, nullptr, dz, flags,
+                    e, stream, &upd, euler ? nullptr : &tupd);
 }

@@ -60,6 +60,7 @@ _PROTOS = {
     "ny_add_laplacian": ([_P, _P, _P, _D, _D, _D, ny_ext, _P], _I),
     "ny_rhs": ([_P] + [_P] * 12 + [_D, _I, ny_ext, _P], _I),
     "ny_rhs_update_u": ([_P] + [_P] * 9 + [C.POINTER(_P * 3)] * 3 + [_I, _D, _D, _I, ny_ext, _P], _I),
+    "ny_rhs_step": ([_P] + [_P] * 7 + [C.POINTER(_P * 4)] * 4 + [_I, _D, _D, _I, ny_ext, _P], _I),
     "ny_ts_axpy": ([_P, _P, _P, _D, _LL, _P], _I),
     "ny_ts_lfam3_first": ([_P, _P, _P, _P, _P, _D, _LL, _P], _I),
     "ny_ts_lfam3_pred": ([_P, _P, _P, _P, _P, _D, _LL, _P], _I),

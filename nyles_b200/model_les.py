@@ -46,7 +46,7 @@ class LES(object):
         self.halo = halo.set_halo(param, self.state)
         self.neighbours = param["neighbours"]
         self.timescheme = ts.Timescheme(param, self.state)
-        self.timescheme.set(self.rhs, self.diagnose_var, self.rhs_update_u)
+        self.timescheme.set(self.rhs, self.diagnose_var, self.rhs_update_u, self.rhs_step, self._rest_rhs)
         self.orderA, self.orderVF, self.orderKE = param["orderA"], param["orderVF"], param["orderKE"]
         self.rotating = param["rotating"]
         self.forced = param["forced"]
@@ -190,6 +190,49 @@ class LES(object):
             self.tracer.rhstrac(state, dstate)
             self.tracer.traclist = saved
         return True
+
+    def rhs_step(self, state, t, mode, dt, stateb, staten, last=False):
+        """rhs() and the time-scheme update of b and u in the two RHS launches themselves (ny_rhs_step;
+        mode 1: LFAM3 start-up, 2: predictor, 3: corrector): no tendency is stored and each field is written
+        once, into the buffer that the scheme no longer needs; the buffers of state / stateb / staten are
+        then rotated (core/timescheme.py:131-175 leaves the same values in the same-named arrays).
+        Returns the names it has updated, or None -- having done nothing -- when something must see the
+        tendencies first (viscosity, forcing) or the fused path is off."""
+        if not self.fused or (last and self.add_viscosity) or self.forced:
+            return None
+        U, w = state.U, state.vor
+        t0 = U["i"].tensor
+        flags = (1 if self.euler else 0) | (0 if self.nonlinear else 2)
+        names = ([] if self.euler else ["b"]) + ["u_i", "u_j", "u_k"]
+        outs = stateb if mode == 3 else staten
+
+        def ptr4(st):
+            p = [lib.ptr(None if self.euler else st.b.tensor).value] + [lib.ptr(st.u[d].tensor).value for d in "ijk"]
+            return lib.C.byref((lib.C.c_void_p * 4)(*p))
+        lib.check(lib.load().ny_rhs_step(
+            lib.context(t0.device), lib.ptr(U["i"].tensor), lib.ptr(U["j"].tensor), lib.ptr(U["k"].tensor),
+            lib.ptr(w["i"].tensor), lib.ptr(w["j"].tensor), lib.ptr(w["k"].tensor), lib.ptr(state.ke.tensor),
+            ptr4(state), ptr4(stateb), ptr4(staten), ptr4(outs), mode, dt, self.grid.dz, flags, lib.ext(t0),
+            lib.stream()))
+        for name in names:
+            S, B, N = state.get(name), stateb.get(name), staten.get(name)
+            if mode == 3:                     # new state <- sb's buffer; sb <- sn (state at n); sn <- scratch
+                S.tensor, B.tensor, N.tensor = B.tensor, N.tensor, S.tensor
+            else:                             # new state <- sn's buffer; sn <- the old state array itself
+                S.tensor, N.tensor = N.tensor, S.tensor
+                if mode == 1:
+                    B.tensor.copy_(N.tensor)
+        return names
+
+    def _rest_rhs(self, state, dstate):
+        """Tendencies of the prognostic scalars that rhs_step does not update itself: the passive tracers
+        (tracer.py:44-72) and, in the Euler model, the buoyancy that nothing moves (db = 0)."""
+        if self.euler:
+            dstate.b.tensor.zero_()
+        if len(self.traclist) > 1:
+            saved, self.tracer.traclist = self.tracer.traclist, self.traclist[1:]
+            self.tracer.rhstrac(state, dstate)
+            self.tracer.traclist = saved
 
     @timing
     def forward(self, t, dt):

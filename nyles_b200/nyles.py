@@ -147,7 +147,8 @@ class Nyles(object):
             d.copy_(h, non_blocking=True)
         dt = self.compute_dt()
         self.model.forward(t, dt)
-        for h, d in zip(host_state, dev):
+        # the fused step rotates the buffers of the prognostic fields: ask again where they live
+        for h, d in zip(host_state, self.prognostic_tensors()):
             h.copy_(d, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return dt

@@ -47,8 +47,17 @@ class FieldView(object):
 
     __array_priority__ = 100
 
-    def __init__(self, tensor):
-        self.tensor = tensor
+    def __init__(self, tensor=None, owner=None, axes=None):
+        # A view taken from a Scalar is bound to the Scalar, not to its current buffer: the fused time
+        # step rotates the buffers of the prognostic fields (model_les.LES.rhs_step), and a view kept
+        # across steps -- as NumPy views of the reference may be -- must keep showing the field.
+        self._tensor, self._owner, self._axes = tensor, owner, axes
+
+    @property
+    def tensor(self):
+        if self._owner is not None:
+            return self._owner.tensor.permute(*self._axes)
+        return self._tensor
 
     # --- conversions
     def _coerce(self, value):
@@ -152,7 +161,7 @@ class Scalar(object):
         if idx not in _AXES:
             raise ValueError("argument idx of Scalar.view must be in ['i','j','k'], not %r" % (idx,))
         self.activeview = idx
-        return FieldView(self.tensor.permute(*_AXES[idx]))
+        return FieldView(owner=self, axes=_AXES[idx])
 
     def flipview(self, idx):
         """Alias with idx as OUTER direction (variables.py:184-204)."""

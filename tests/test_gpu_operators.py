@@ -221,6 +221,61 @@ def test_fused_rhs_equals_operator_sequence(K, L, shape, flags):
         assert np.array_equal(a, host(t))
 
 
+@pytest.mark.parametrize("shape", SHAPES[1:] + [(40, 37, 70)])
+@pytest.mark.parametrize("mode", [1, 2, 3])
+@pytest.mark.parametrize("flags", [0, 1, 2])
+def test_rhs_step_equals_rhs_then_timescheme(L, shape, mode, flags):
+    """ny_rhs_step (the RHS kernels apply the LFAM3 / Euler update and write each field once, into a
+    separate buffer) against ny_rhs followed by the ny_ts_* kernels: bit-identical new state, and none
+    of the arrays it only reads is touched."""
+    euler = flags & 1
+    b, ke, sb_b, sn_b = rand_fields(shape, 4, 40)
+    U, w, u, ub, un = (rand_fields(shape, 3, 41 + n) for n in range(5))
+    dz, dt = 0.25, 0.0137
+    lib = L.load()
+    g = lambda a: dev(a)                                     # noqa: E731
+    gU, gw, gke = [g(a) for a in U], [g(a) for a in w], g(ke)
+    # reference sequence: tendencies, then the elementwise update of every field
+    s = [g(b)] + [g(a) for a in u]
+    sb = [g(sb_b)] + [g(a) for a in ub]
+    sn = [g(sn_b)] + [g(a) for a in un]
+    ds = [torch.zeros(shape, dtype=torch.float64, device="cuda") for _ in range(4)]
+    L.check(lib.ny_rhs(L.context(), L.ptr(s[0]), *[L.ptr(t) for t in gU + gw], L.ptr(gke), L.ptr(ds[0]),
+                       *[L.ptr(t) for t in ds[1:]], dz, flags, L.ext(s[0]), L.stream()))
+    fields = range(1, 4) if euler else range(4)
+    for f in fields:
+        n = s[f].numel()
+        if mode == 1:
+            L.check(lib.ny_ts_lfam3_first(L.context(), L.ptr(s[f]), L.ptr(ds[f]), L.ptr(sb[f]), L.ptr(sn[f]), dt, n, L.stream()))
+        elif mode == 2:
+            L.check(lib.ny_ts_lfam3_pred(L.context(), L.ptr(s[f]), L.ptr(ds[f]), L.ptr(sb[f]), L.ptr(sn[f]), dt, n, L.stream()))
+        else:
+            L.check(lib.ny_ts_lfam3_corr(L.context(), L.ptr(s[f]), L.ptr(ds[f]), L.ptr(sn[f]), dt, n, L.stream()))
+    # fused, rotating form
+    s2 = [g(b)] + [g(a) for a in u]
+    sb2 = [g(sb_b)] + [g(a) for a in ub]
+    sn2 = [g(sn_b)] + [g(a) for a in un]
+    out = [torch.full(shape, 9.0, dtype=torch.float64, device="cuda") for _ in range(4)]
+
+    def ptr4(ts):
+        return C.byref((C.c_void_p * 4)(*[None if (euler and n == 0) else L.ptr(t).value for n, t in enumerate(ts)]))
+    L.check(lib.ny_rhs_step(L.context(), *[L.ptr(t) for t in gU + gw], L.ptr(gke), ptr4(s2), ptr4(sb2), ptr4(sn2),
+                            ptr4(out), mode, dt, dz, flags, L.ext(s2[0]), L.stream()))
+    for f in fields:
+        assert np.array_equal(host(out[f]), host(s[f])), "field %d" % f
+        # read-only inputs stay as they were
+        assert np.array_equal(host(s2[f]), (b if f == 0 else u[f - 1]))
+        assert np.array_equal(host(sb2[f]), (sb_b if f == 0 else ub[f - 1]))
+        assert np.array_equal(host(sn2[f]), (sn_b if f == 0 else un[f - 1]))
+    # what the rotation of the caller relies on: after modes 1 and 2 the old state array equals sn (and sb)
+    if mode in (1, 2):
+        for f in fields:
+            assert np.array_equal(host(sn[f]), host(s2[f])) and np.array_equal(host(sb[f]), host(s2[f]))
+    # aliasing the output with an array the launch reads is refused
+    assert lib.ny_rhs_step(L.context(), *[L.ptr(t) for t in gU + gw], L.ptr(gke), ptr4(s2), ptr4(sb2), ptr4(sn2),
+                           ptr4(s2 if mode != 3 else sn2), mode, dt, dz, flags, L.ext(s2[0]), L.stream()) != 0
+
+
 @pytest.mark.parametrize("shape", SHAPES[:3])
 def test_add_laplacian(K, L, shape):
     phi, dphi = rand_fields(shape, 2, 40)
