@@ -33,6 +33,7 @@ constexpr int MAXLEV = 50;
 constexpr int NH = 3;
 constexpr int MAX_PARTIALS = 1 << 15;
 long long g_gather_cells = 262144;         // levels with at most this many cells are gathered (64^3)
+long long g_split_tiles = 148;            // levels with at least this many 58 x 24 tiles launch wall-free tiles separately
 long long g_overlap_cells = 1LL << 25;     // slab levels with at least this many local cells overlap their halo exchange
 
 struct Level {
@@ -63,6 +64,7 @@ struct ny_mg {
     ny_comm* comm;
     LevelMaps maps[50];
     int fused;                             // use the fused V-cycle legs where a level allows them
+    int split_tiles;                       // fused legs: wall-free tiles run the specialised kernel instance
     int halo_ok;                           // periodic / slab halos of x and b of level 1 are consistent
     int ysync;                             // wall-halo cells of y equal those of x on every level
     int nranks, rank;
@@ -553,7 +555,7 @@ k_smooth2(const double* __restrict__ x, const double* __restrict__ b, double* __
 }
 
 // ---- residual on the interior with analytic diag; what happens to r depends on MODE ------------
-enum { RS_STORE, RS_NORM, RS_NORMB };
+enum { RS_STORE, RS_NORM, RS_NORMB, RS_NORM2 };   // RS_NORM2: sum r^2 and sum b^2 in one pass over b
 // block (32,8): tile 32 x 8 of the interior, marching over a chunk of planes
 template <int MODE>
 __global__ void __launch_bounds__(256)
@@ -565,7 +567,7 @@ k_resid(const double* __restrict__ x, const double* __restrict__ b, double* __re
     const int aj = NH + blockIdx.y * 8 + threadIdx.y;
     const int k0 = NH + blockIdx.z * kchunk, k1 = min(k0 + kchunk, g.nz - NH);
     const bool act = ai < g.nx + NH && aj < g.ny + NH;
-    double acc = 0.0;
+    double acc = 0.0, accb = 0.0;
     if (act) {
         const int cxy = cnt_xy(g, ai, aj);
         const long long o = (long long)aj * g.sj + ai;
@@ -578,8 +580,10 @@ k_resid(const double* __restrict__ x, const double* __restrict__ b, double* __re
                 const double xp = x[c + g.sk];
                 const double s = x[c - 1] + x[c + 1] + x[c - g.sj] + x[c + g.sj] + xm + xp;
                 const double diag = (double)(cxy + cnt_z(g, k));
-                const double rv = b[c] + diag * xc - s;
+                const double bv = b[c];
+                const double rv = bv + diag * xc - s;
                 if (MODE == RS_STORE) r[c] = rv; else acc = acc + rv * rv;
+                if (MODE == RS_NORM2) accb = accb + bv * bv;
                 xm = xc; xc = xp;
             }
         }
@@ -589,10 +593,22 @@ k_resid(const double* __restrict__ x, const double* __restrict__ b, double* __re
         for (int o = 16; o > 0; o >>= 1) acc = acc + __shfl_xor_sync(0xffffffffu, acc, o);
         if ((tid & 31) == 0) sh[tid >> 5] = acc;
         __syncthreads();
+        const long long slot = ((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
         if (tid == 0) {
             double t = 0.0;
             for (int w = 0; w < 8; w++) t = t + sh[w];
-            partial[((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = t;
+            partial[slot] = t;
+        }
+        if (MODE == RS_NORM2) {          // the same tree for sum b^2; its partials follow those of sum r^2
+            __syncthreads();
+            for (int o = 16; o > 0; o >>= 1) accb = accb + __shfl_xor_sync(0xffffffffu, accb, o);
+            if ((tid & 31) == 0) sh[tid >> 5] = accb;
+            __syncthreads();
+            if (tid == 0) {
+                double t = 0.0;
+                for (int w = 0; w < 8; w++) t = t + sh[w];
+                partial[(long long)gridDim.x * gridDim.y * gridDim.z + slot] = t;
+            }
         }
     }
 }
@@ -935,12 +951,16 @@ int prolongation(ny_mg* mg, cudaStream_t st, int lev)
 }
 
 // enqueue the global sum of the per-block partials into d_red[MAX_PARTIALS + slot]
-int finish_sum(ny_mg* mg, cudaStream_t st, int nparts, int slot)
+int finish_sum(ny_mg* mg, cudaStream_t st, int nparts, int slot, int first = 0)
 {
-    k_sum_final<<<1, 256, 0, st>>>(mg->d_red, nparts, mg->d_red + MAX_PARTIALS + slot);
+    k_sum_final<<<1, 256, 0, st>>>(mg->d_red + first, nparts, mg->d_red + MAX_PARTIALS + slot);
     LAUNCH_OK(mg);
     return ny_comm_allreduce(mg->comm, mg->d_red + MAX_PARTIALS + slot, 1, 0, st);
 }
+
+// sum(msk*b^2) -> slot 0 and, after residual(1), sum(msk*r^2) -> slot 1, from one pass over x and b
+// (same per-thread order and reduction trees as the two separate passes: same bits)
+int norm_b_and_r_async(ny_mg* mg, cudaStream_t st);
 
 // sum(msk*b^2) of level 1 -> slot 0
 int norm_b_async(ny_mg* mg, cudaStream_t st)
@@ -981,6 +1001,21 @@ int norm_r_async(ny_mg* mg, cudaStream_t st)
     return finish_sum(mg, st, nparts, 1);
 }
 
+int norm_b_and_r_async(ny_mg* mg, cudaStream_t st)
+{
+    Level& L = mg->lev[0];
+    March m = march_geom(mg, L.nx, L.ny, L.nz - 2 * mg->nh);
+    if (!mg->box || 2 * m.nparts > MAX_PARTIALS) {
+        TRY(norm_b_async(mg, st));
+        return norm_r_async(mg, st);
+    }
+    ny_prof_scope ps(mg->ctx, NY_PROF_MG_NORM, st);
+    k_resid<RS_NORM2><<<m.grid, dim3(32, 8), 0, st>>>(L.x, L.b, nullptr, box_of(mg, L), m.chunk, mg->d_red);
+    LAUNCH_OK(mg);
+    TRY(finish_sum(mg, st, m.nparts, 0, m.nparts));
+    return finish_sum(mg, st, m.nparts, 1);
+}
+
 // ---- fused V-cycle legs (ny_mg_vleg.cuh) ---------------------------------------------------------
 // A level runs the fused legs when the analytic box coefficients are valid, its interior is at least
 // as wide as the halo in every direction (so that all three halo rings are plain copies) and -- for
@@ -1007,11 +1042,11 @@ int sync_y(ny_mg* mg, cudaStream_t st)
 
 struct LegGeom { dim3 grid; int chunk; int nparts; };
 // launch geometry for the interior planes [0, nzi) of a level cut into chunks
-inline LegGeom leg_geom(ny_mg* mg, const Level& L, int nzi, int tj, int extra, bool even)
+inline LegGeom leg_geom(ny_mg* mg, const Level& L, int nzi, int tj, int extra, bool even, long long ntiles = 0)
 {
     LegGeom q;
     const int gx = (L.nx + VL_TI - 1) / VL_TI, gy = (L.ny + tj - 1) / tj;
-    const long long tiles = (long long)gx * gy, sms = mg->ctx->num_sms;
+    const long long tiles = ntiles > 0 ? ntiles : (long long)gx * gy, sms = mg->ctx->num_sms;
     // chunks of planes: minimise (waves of CTAs) x (planes marched per CTA, including the pipeline fill)
     int best = 1;
     long long best_cost = -1;
@@ -1026,8 +1061,36 @@ inline LegGeom leg_geom(ny_mg* mg, const Level& L, int nzi, int tj, int extra, b
     q.chunk = best;
     const int gz = (nzi + best - 1) / best;
     q.grid = dim3(gx, gy, gz);
-    q.nparts = gx * gy * gz;
+    q.nparts = (int)(tiles * gz);
     return q;
+}
+
+// Tiles of a level whose 64 x 32 region keeps clear of the x / y walls and whose coarse tile lies inside the
+// coarse domain (the INT instance of k_vleg): the rectangle [bx0, bx0+nbx) x [by0, by0+nby) of the tile grid.
+inline TileMap interior_tiles(const ny_mg* mg, const Level& L, int tj, int apron_top)
+{
+    TileMap m;
+    const int gx = (L.nx + VL_TI - 1) / VL_TI, gy = (L.ny + tj - 1) / tj;
+    m.mode = 1; m.gx = gx;
+    int x0 = 0, x1 = gx, y0 = 0, y1 = gy;
+    if (!mg->xper) {
+        // columns RX0 .. RX0+VL_RI-1 and both neighbours inside [NH, nx+NH): RX0 >= NH+1, RX0+VL_RI <= nx+NH-1
+        x0 = gx; x1 = 0;
+        for (int b = 0; b < gx; b++) {
+            const int RX0 = b * VL_TI;
+            if (RX0 >= NH + 1 && RX0 + VL_RI <= L.nx + NH - 1) { if (b < x0) x0 = b; x1 = b + 1; }
+        }
+    }
+    if (!mg->yper) {
+        y0 = gy; y1 = 0;
+        for (int b = 0; b < gy; b++) {
+            const int RY0 = NH + b * tj - apron_top;
+            if (RY0 >= NH + 1 && RY0 + VL_RJ <= L.ny + NH - 1) { if (b < y0) y0 = b; y1 = b + 1; }
+        }
+    }
+    m.bx0 = x0; m.nbx = x1 > x0 ? x1 - x0 : 0;
+    m.by0 = y0; m.nby = y1 > y0 ? y1 - y0 : 0;
+    return m;
 }
 
 constexpr int LEG_EDGE = 8;      // planes next to a slab neighbour that are computed first (even, >= 2 * NH)
@@ -1041,7 +1104,8 @@ int launch_leg(ny_mg* mg, cudaStream_t st, int lev, const Level& V, bool* exchan
     using LY = VlegLayout<PRO, POST>;
     static bool attr_set = false;
     if (!attr_set) {
-        NY_CUDA(cudaFuncSetAttribute(k_vleg<PRO, POST>, cudaFuncAttributeMaxDynamicSharedMemorySize, LY::bytes));
+        NY_CUDA(cudaFuncSetAttribute(k_vleg<PRO, POST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LY::bytes));
+        NY_CUDA(cudaFuncSetAttribute(k_vleg<PRO, POST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LY::bytes));
         attr_set = true;
     }
     Level& F = mg->lev[lev - 1];
@@ -1053,11 +1117,36 @@ int launch_leg(ny_mg* mg, cudaStream_t st, int lev, const Level& V, bool* exchan
     const Box gf = box_of(mg, F), gv = box_of(mg, V);
     const CUtensorMap& tmc = PRO ? mg->maps[lev].cx : M.x;
     int nparts = 0;
+    // tiles away from the x / y walls run the INT instance, the frame around them the general one
+    TileMap inner = interior_tiles(mg, F, LY::tj, LY::apron_top);
+    const int tgx = (F.nx + VL_TI - 1) / VL_TI, tgy = (F.ny + LY::tj - 1) / LY::tj;
+    const long long n_inner = (long long)inner.nbx * inner.nby, n_frame = (long long)tgx * tgy - n_inner;
     auto launch = [&](int kz0, int kz1, cudaStream_t s) -> int {
+        // (two launches only pay where each fills the machine several times: the large levels)
+        if (n_inner > 0 && mg->split_tiles && n_inner + n_frame >= g_split_tiles) {
+            LegGeom q = leg_geom(mg, F, kz1 - kz0, LY::tj, extra, POST == POST_RESTRICT, n_inner);
+            LegGeom qf = leg_geom(mg, F, kz1 - kz0, LY::tj, extra, POST == POST_RESTRICT, n_frame > 0 ? n_frame : 1);
+            if (POST == POST_NORM && nparts + q.nparts + qf.nparts > MAX_PARTIALS) { ny_set_error("too many partial sums"); return NY_ERR_ARG; }
+            k_vleg<PRO, POST, true><<<dim3(inner.nbx, inner.nby, q.grid.z), VL_NW * 32, LY::bytes, s>>>(
+                M.x, M.b, tmc, F.y, V.b, mg->d_red + nparts, gf, gv, omega, cff1, q.chunk, kz0, kz1, inner);
+            LAUNCH_OK(mg);
+            nparts += q.nparts;
+            if (n_frame > 0) {
+                TileMap fr = inner;
+                fr.mode = 2;
+                k_vleg<PRO, POST, false><<<dim3((unsigned)n_frame, 1, qf.grid.z), VL_NW * 32, LY::bytes, s>>>(
+                    M.x, M.b, tmc, F.y, V.b, mg->d_red + nparts, gf, gv, omega, cff1, qf.chunk, kz0, kz1, fr);
+                LAUNCH_OK(mg);
+                nparts += qf.nparts;
+            }
+            return NY_OK;
+        }
         const LegGeom q = leg_geom(mg, F, kz1 - kz0, LY::tj, extra, POST == POST_RESTRICT);
         if (POST == POST_NORM && nparts + q.nparts > MAX_PARTIALS) { ny_set_error("too many partial sums"); return NY_ERR_ARG; }
-        k_vleg<PRO, POST><<<q.grid, VL_NW * 32, LY::bytes, s>>>(M.x, M.b, tmc, F.y, V.b, mg->d_red + nparts, gf, gv, omega,
-                                                                cff1, q.chunk, kz0, kz1);
+        TileMap all = inner;
+        all.mode = 0;
+        k_vleg<PRO, POST, false><<<q.grid, VL_NW * 32, LY::bytes, s>>>(M.x, M.b, tmc, F.y, V.b, mg->d_red + nparts, gf, gv, omega,
+                                                                       cff1, q.chunk, kz0, kz1, all);
         LAUNCH_OK(mg);
         nparts += q.nparts;
         return NY_OK;
@@ -1317,6 +1406,7 @@ int create(ny_ctx* ctx, ny_comm* comm, int nx, int ny, int nz_global, int topolo
         }
     }
     mg->fused = 1;
+    mg->split_tiles = 1;
     mg->halo_ok = 0;
     mg->ysync = 1;                                              // x and y are both zero
     for (int l = 0; l < mg->nlevels; l++) {
@@ -1394,6 +1484,7 @@ extern "C" int ny_mg_create_slab(ny_ctx* ctx, ny_comm* comm, int nx, int ny, int
 
 extern "C" void ny_mg_set_gather_cells(long long cells) { g_gather_cells = cells; }
 extern "C" void ny_mg_set_overlap_cells(long long cells) { g_overlap_cells = cells; }
+extern "C" void ny_mg_set_split_tiles(long long tiles) { g_split_tiles = tiles; }
 
 extern "C" int ny_mg_nlevels(ny_mg* mg) { return mg ? mg->nlevels : 0; }
 extern "C" int ny_mg_is_box(ny_mg* mg) { return mg ? mg->box : 0; }
@@ -1413,6 +1504,7 @@ extern "C" int ny_mg_set_fused_legs(ny_mg* mg, int on)
 {
     NY_REQUIRE(mg, "null argument");
     mg->fused = on ? 1 : 0;
+    mg->split_tiles = on == 2 ? 0 : 1;      // 2: fused legs, every tile through the general kernel instance
     return NY_OK;
 }
 
@@ -1468,8 +1560,7 @@ extern "C" int ny_mg_solve(ny_mg* mg, ny_mg_stats* stats, void* stream)
     double hist[32];
     // normb = sum(msk b^2); res = sum(msk r^2)/normb after residual(1)   (operators.f90:81-125)
     // both are enqueued before the first host read: one synchronisation instead of two
-    TRY(norm_b_async(mg, st));
-    TRY(norm_r_async(mg, st));
+    TRY(norm_b_and_r_async(mg, st));
     TRY(read_scalars(mg, st, 2));
     const double normb = mg->ctx->h_pinned[0];
     double res = normb > 0.0 ? mg->ctx->h_pinned[1] / normb : 0.0;

@@ -76,7 +76,11 @@ struct VlegCtx {
 // One plane of the pipeline.  FAST: every stage runs, the three planes involved have both k-neighbours
 // inside the domain and the plane written lies in the chunk -- no tests left but the per-cell domain
 // flags.  The roles (minus, centre, plus) of the register sets rotate statically in the caller.
-template <bool PRO, int POST, bool FAST>
+// INT: no cell of the CTA's region lies on or next to an x / y wall, and every coarse cell the prolongation
+// reads is inside the domain: each in-plane neighbour count is 4, so 1/diag, diag and Pcoef depend on the
+// plane only (CTA-uniform) and no per-cell domain flag is left.  These tiles -- the bulk of a large level --
+// are launched as their own kernel instance, whose register allocation is free of the per-cell constants.
+template <bool PRO, int POST, bool FAST, bool INT>
 __device__ __forceinline__ void vleg_plane(const VlegCtx& c, int p, int t, const P4& xm, const P4& xc, P4& xp,
                                            const P4& ym, const P4& yc, P4& yp, const P4& zm, const P4& zc, P4& zp,
                                            P4& bp, const P4& b1, const P4& b2, double& acc, double& rsum)
@@ -101,10 +105,20 @@ __device__ __forceinline__ void vleg_plane(const VlegCtx& c, int p, int t, const
         const double pbA1 = 9 * b01 + 3 * b00 + 3 * b11 + b10, poA1 = 9 * o01 + 3 * o00 + 3 * o11 + o10;
         const double pbB0 = 9 * b10 + 3 * b11 + 3 * b00 + b01, poB0 = 9 * o10 + 3 * o11 + 3 * o00 + o01;
         const double pbB1 = 9 * b11 + 3 * b10 + 3 * b01 + b00, poB1 = 9 * o11 + 3 * o10 + 3 * o01 + o00;
-        if (fz && c.cA0 >= 0) xp.A.x = xp.A.x + c.s_pcoef[c.exA0 + ez] * (3 * pbA0 + poA0);
-        if (fz && c.cA1 >= 0) xp.A.y = xp.A.y + c.s_pcoef[c.exA1 + ez] * (3 * pbA1 + poA1);
-        if (fz && c.cB0 >= 0) xp.B.x = xp.B.x + c.s_pcoef[c.exB0 + ez] * (3 * pbB0 + poB0);
-        if (fz && c.cB1 >= 0) xp.B.y = xp.B.y + c.s_pcoef[c.exB1 + ez] * (3 * pbB1 + poB1);
+        if (INT) {
+            if (fz) {
+                const double pc = FAST ? 1.0 / 64.0 : c.s_pcoef[2 + ez];
+                xp.A.x = xp.A.x + pc * (3 * pbA0 + poA0);
+                xp.A.y = xp.A.y + pc * (3 * pbA1 + poA1);
+                xp.B.x = xp.B.x + pc * (3 * pbB0 + poB0);
+                xp.B.y = xp.B.y + pc * (3 * pbB1 + poB1);
+            }
+        } else {
+            if (fz && c.cA0 >= 0) xp.A.x = xp.A.x + c.s_pcoef[c.exA0 + ez] * (3 * pbA0 + poA0);
+            if (fz && c.cA1 >= 0) xp.A.y = xp.A.y + c.s_pcoef[c.exA1 + ez] * (3 * pbA1 + poA1);
+            if (fz && c.cB0 >= 0) xp.B.x = xp.B.x + c.s_pcoef[c.exB0 + ez] * (3 * pbB0 + poB0);
+            if (fz && c.cB1 >= 0) xp.B.y = xp.B.y + c.s_pcoef[c.exB1 + ez] * (3 * pbB1 + poB1);
+        }
         st2(px + oA, xp.A);             // the rows above / below read the prolonged plane in the next iteration
         st2(px + oB, xp.B);
         nytma::fence_proxy_async();
@@ -113,7 +127,10 @@ __device__ __forceinline__ void vleg_plane(const VlegCtx& c, int p, int t, const
         bp.A = ld2(pbc + oA); bp.B = ld2(pbc + oB);
         const double2 up = ld2(pxc + c.oUp), dn = ld2(pxc + c.oDn);
         const int cz = FAST ? 2 : cnt_z(g, p);
-        if (cz == 2)
+        if (INT) {
+            const double rc = cz == 2 ? 1.0 / 6.0 : c.s_recip[max(4 + cz, 0)];
+            sweep_patch(xc.A, xc.B, xm.A, xm.B, xp.A, xp.B, up, dn, bp.A, bp.B, rc, rc, rc, rc, c.omega, c.cff1, yp.A, yp.B);
+        } else if (cz == 2)
             sweep_patch(xc.A, xc.B, xm.A, xm.B, xp.A, xp.B, up, dn, bp.A, bp.B, c.rA0, c.rA1, c.rB0, c.rB1,
                         c.omega, c.cff1, yp.A, yp.B);
         else                            // planes next to the k ends (CTA-uniform)
@@ -129,7 +146,10 @@ __device__ __forceinline__ void vleg_plane(const VlegCtx& c, int p, int t, const
         const double* const py = c.sy + (q & 1) * VL_PLANE;
         const double2 up = ld2(py + c.oUp), dn = ld2(py + c.oDn);
         const int cz = FAST ? 2 : cnt_z(g, q);
-        if (cz == 2)
+        if (INT) {
+            const double rc = cz == 2 ? 1.0 / 6.0 : c.s_recip[max(4 + cz, 0)];
+            sweep_patch(yc.A, yc.B, ym.A, ym.B, yp.A, yp.B, up, dn, b1.A, b1.B, rc, rc, rc, rc, c.omega, c.cff1, zp.A, zp.B);
+        } else if (cz == 2)
             sweep_patch(yc.A, yc.B, ym.A, ym.B, yp.A, yp.B, up, dn, b1.A, b1.B, c.rA0, c.rA1, c.rB0, c.rB1,
                         c.omega, c.cff1, zp.A, zp.B);
         else
@@ -137,10 +157,14 @@ __device__ __forceinline__ void vleg_plane(const VlegCtx& c, int p, int t, const
                         c.s_recip[max(c.cA1 + cz, 0)], c.s_recip[max(c.cB0 + cz, 0)], c.s_recip[max(c.cB1 + cz, 0)],
                         c.omega, c.cff1, zp.A, zp.B);
         const bool qz = FAST ? true : in_z(g, q);
-        if (!(qz && c.cA0 >= 0)) zp.A.x = xm.A.x;            // outside the domain: x is kept
-        if (!(qz && c.cA1 >= 0)) zp.A.y = xm.A.y;
-        if (!(qz && c.cB0 >= 0)) zp.B.x = xm.B.x;
-        if (!(qz && c.cB1 >= 0)) zp.B.y = xm.B.y;
+        if (INT) {
+            if (!qz) { zp.A = xm.A; zp.B = xm.B; }           // a plane outside the domain: x is kept
+        } else {
+            if (!(qz && c.cA0 >= 0)) zp.A.x = xm.A.x;        // outside the domain: x is kept
+            if (!(qz && c.cA1 >= 0)) zp.A.y = xm.A.y;
+            if (!(qz && c.cB0 >= 0)) zp.B.x = xm.B.x;
+            if (!(qz && c.cB1 >= 0)) zp.B.y = xm.B.y;
+        }
         if (POST != POST_NONE) {
             double* const pz = c.sz + (q & 1) * VL_PLANE;
             st2(pz + oA, zp.A);
@@ -171,10 +195,10 @@ __device__ __forceinline__ void vleg_plane(const VlegCtx& c, int p, int t, const
         const double sB0 = lB + zc.B.y + zc.A.x + dn.x + zm.B.x + zp.B.x;
         const double sB1 = zc.B.x + rgB + zc.A.y + dn.y + zm.B.y + zp.B.y;
         const int cz = FAST ? 2 : cnt_z(g, q);
-        const double r0 = b2.A.x + (double)(c.cA0 + cz) * zc.A.x - sA0;
-        const double r1 = b2.A.y + (double)(c.cA1 + cz) * zc.A.y - sA1;
-        const double r2 = b2.B.x + (double)(c.cB0 + cz) * zc.B.x - sB0;
-        const double r3 = b2.B.y + (double)(c.cB1 + cz) * zc.B.y - sB1;
+        const double r0 = b2.A.x + (INT ? (double)(4 + cz) : (double)(c.cA0 + cz)) * zc.A.x - sA0;
+        const double r1 = b2.A.y + (INT ? (double)(4 + cz) : (double)(c.cA1 + cz)) * zc.A.y - sA1;
+        const double r2 = b2.B.x + (INT ? (double)(4 + cz) : (double)(c.cB0 + cz)) * zc.B.x - sB0;
+        const double r3 = b2.B.y + (INT ? (double)(4 + cz) : (double)(c.cB1 + cz)) * zc.B.y - sB1;
         if (POST == POST_NORM) {
             if (FAST || q < c.k1) {     // fnorm, basicoperators.f90:422-440 (interior cells, msk = 1)
                 double a = 0.0;
@@ -202,11 +226,34 @@ __device__ __forceinline__ void vleg_plane(const VlegCtx& c, int p, int t, const
     }
 }
 
-template <bool PRO, int POST>
+// Which tiles of the plane a launch covers.  mode 0: all of them, (blockIdx.x, blockIdx.y) is the tile.
+// mode 1: the rectangle [bx0, bx0+nbx) x [by0, by0+nby), grid (nbx, nby, .).  mode 2: the frame around that
+// rectangle, tiles enumerated along blockIdx.x (rows above, the two side strips, rows below), grid (n, 1, .).
+struct TileMap { int mode, bx0, by0, nbx, nby, gx; };
+
+__device__ __forceinline__ void tile_of(const TileMap& m, int& bx, int& by)
+{
+    if (m.mode == 0) { bx = blockIdx.x; by = blockIdx.y; return; }
+    if (m.mode == 1) { bx = m.bx0 + blockIdx.x; by = m.by0 + blockIdx.y; return; }
+    int idx = blockIdx.x;
+    const int top = m.by0 * m.gx, side = m.gx - m.nbx;
+    if (idx < top) { by = idx / m.gx; bx = idx - by * m.gx; return; }
+    idx -= top;
+    if (idx < m.nby * side) {
+        const int row = idx / side, r = idx - row * side;
+        by = m.by0 + row; bx = r < m.bx0 ? r : r + m.nbx;
+        return;
+    }
+    idx -= m.nby * side;
+    by = m.by0 + m.nby + idx / m.gx; bx = idx % m.gx;
+}
+
+template <bool PRO, int POST, bool INT>
 __global__ void __launch_bounds__(VL_NW * 32, 1)
 k_vleg(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmb,
        const __grid_constant__ CUtensorMap tmc, double* __restrict__ xo, double* __restrict__ bc,
-       double* __restrict__ partial, Box g, Box gc, double omega, double cff1, int kchunk, int kz0, int kz1)
+       double* __restrict__ partial, Box g, Box gc, double omega, double cff1, int kchunk, int kz0, int kz1,
+       TileMap tm)
 {
     // the launch covers the interior planes [kz0, kz1) (0-based) of the level in chunks of kchunk planes
     using LY = VlegLayout<PRO, POST>;
@@ -223,8 +270,10 @@ k_vleg(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensor
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int e = 2 * lane, rA = 2 * warp;
-    const int RX0 = (int)blockIdx.x * VL_TI;                            // array column of region column 0 (even)
-    const int RY0 = NH + (int)blockIdx.y * TJ - APT;                    // array row of region row 0
+    int tbx, tby;
+    tile_of(tm, tbx, tby);
+    const int RX0 = tbx * VL_TI;                                        // array column of region column 0 (even)
+    const int RY0 = NH + tby * TJ - APT;                                // array row of region row 0
     const int k0 = NH + kz0 + (int)blockIdx.z * kchunk, k1 = min(k0 + kchunk, NH + kz1);   // stored planes [k0, k1)
     // first iteration that runs sweep 1 / sweep 2 / the residual, first and last iteration, first plane loaded
     const int pb1 = k0 - 1 - NPOST, pb2 = k0 + 1 - NPOST, pb3 = k0 + 2;
@@ -319,9 +368,9 @@ k_vleg(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensor
         __syncthreads(); /* plane t landed; everything written in the last iteration is visible */                  \
         if (threadIdx.x == 0 && t + 2 < nplanes) issue(t + 2);                                                      \
         if (p >= fast_lo && p <= fast_hi)                                                                           \
-            vleg_plane<PRO, POST, true>(c, p, t, X##m, X##c_, X##n, Y##m, Y##c_, Y##n, Z##m, Z##c_, Z##n, B##n, B##c_, B##m, acc, rsum); \
+            vleg_plane<PRO, POST, true, INT>(c, p, t, X##m, X##c_, X##n, Y##m, Y##c_, Y##n, Z##m, Z##c_, Z##n, B##n, B##c_, B##m, acc, rsum); \
         else                                                                                                        \
-            vleg_plane<PRO, POST, false>(c, p, t, X##m, X##c_, X##n, Y##m, Y##c_, Y##n, Z##m, Z##c_, Z##n, B##n, B##c_, B##m, acc, rsum); \
+            vleg_plane<PRO, POST, false, INT>(c, p, t, X##m, X##c_, X##n, Y##m, Y##c_, Y##n, Z##m, Z##c_, Z##n, B##n, B##c_, B##m, acc, rsum); \
         p++;                                                                                                        \
     }
     for (;;) {

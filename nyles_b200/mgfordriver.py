@@ -146,8 +146,9 @@ class MG(object):
         lib.check(self.L.ny_mg_set_fast_path(self.mg, 1 if on else 0))
 
     def set_fused_legs(self, on):
-        """on=False: V-cycles use one box kernel per operator instead of the fused legs."""
-        lib.check(self.L.ny_mg_set_fused_legs(self.mg, 1 if on else 0))
+        """on=False: V-cycles use one box kernel per operator instead of the fused legs; on=2: fused legs
+        with every tile through the general kernel instance (no wall-free specialisation)."""
+        lib.check(self.L.ny_mg_set_fused_legs(self.mg, int(on)))
 
     def op(self, name, lev=1):
         code = dict(smooth=1, residual=2, restriction=3, prolongation=4, vcycle=5, fill=6)[name]

@@ -182,16 +182,22 @@ def test_box_kernels_equal_generic_kernels(grid):
     assert torch.equal(xf, xs)
 
 
+@pytest.mark.parametrize("split", [1, 2])
 @pytest.mark.parametrize("grid", [(128, 64, 96, 1), (64, 128, 32, 1), (96, 32, 64, 1), (64, 64, 64, 5), (128, 32, 64, 6),
-                                  (16, 16, 16, 6), (8, 8, 8, 1)])
-def test_fused_legs_equal_single_operator_kernels(grid):
+                                  (16, 16, 16, 6), (8, 8, 8, 1), (256, 128, 128, 1), (128, 256, 128, 5), (128, 128, 256, 6)])
+def test_fused_legs_equal_single_operator_kernels(grid, split):
     """The TMA-staged fused V-cycle legs (smooth+residual+restriction, prolongation+smooth[+norm]) against
     the one-box-kernel-per-operator V-cycle, bit for bit, on grids whose tiles are ragged in every direction:
     single V-cycles from random x (halos included) and b, then complete solves with warm starts."""
     from nyles_b200.mgfordriver import MG
+    from nyles_b200 import lib
     nx, ny, nz, topo = grid
+    lib.load().ny_mg_set_split_tiles(1)            # test grids are small: split wherever a wall-free tile exists
     fused, plain = MG(1, 1, nx, ny, nz, 3, topo), MG(1, 1, nx, ny, nz, 3, topo)
     plain.set_fused_legs(False)
+    # split 1 (default): tiles away from the x / y walls run the specialised (wall-free) kernel instance,
+    # the frame around them the general one; split 2: every tile through the general instance
+    fused.set_fused_legs(split)
     gen = torch.Generator(device="cuda").manual_seed(21)
     shape = fused.get_arrayshape(1)
     for rep in range(2):
@@ -217,3 +223,4 @@ def test_fused_legs_equal_single_operator_kernels(grid):
         assert fused.stats["nite"] == plain.stats["nite"] and fused.stats["nite"] > 0
         np.testing.assert_allclose(fused.stats["res"], plain.stats["res"], rtol=1e-11, atol=0)
         assert torch.equal(xf, xp)
+    lib.load().ny_mg_set_split_tiles(148)
