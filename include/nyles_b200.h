@@ -240,6 +240,9 @@ void ny_mg_set_overlap_cells(long long cells);
 /* fused legs: levels whose plane holds at least `tiles` 58 x 24 tiles launch the tiles that keep clear of the
  * x / y walls as a separate, wall-free kernel instance (default 148 = one per SM; tests lower it) */
 void ny_mg_set_split_tiles(long long tiles);
+/* closed boxes: the levels with at most `cells` cells (default 4096 = 16^3) form the tail of the V-cycle that
+ * one single-CTA launch runs from the first smoothing down to the coarsest level and back (0: off) */
+void ny_mg_set_tail_cells(long long cells);
 void ny_mg_destroy(ny_mg*);
 int  ny_mg_nlevels(ny_mg*);
 /* 1 if the mask is the default box, so that the fused analytic-coefficient kernels are in use */
@@ -249,7 +252,8 @@ int  ny_mg_is_box(ny_mg*);
 int  ny_mg_set_fast_path(ny_mg*, int on);
 /* on = 0: V-cycles run one box kernel per operator; on = 1 (default): the fused TMA-staged legs
  * (smooth+residual+restriction, prolongation+smooth[+norm]) wherever a level allows them, tiles away from
- * the x / y walls through the wall-free kernel instance; on = 2: fused legs, general instance for every tile */
+ * the x / y walls through the wall-free kernel instance and the smallest levels of a closed box in one launch;
+ * on = 2: fused legs, general instance for every tile, no one-launch tail */
 int  ny_mg_set_fused_legs(ny_mg*, int on);
 /* 1-based index of the first level that is replicated on every rank (1 on a single rank) */
 int  ny_mg_first_gathered_level(ny_mg*);

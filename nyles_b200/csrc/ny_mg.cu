@@ -33,6 +33,7 @@ constexpr int MAXLEV = 50;
 constexpr int NH = 3;
 constexpr int MAX_PARTIALS = 1 << 15;
 long long g_gather_cells = 262144;         // levels with at most this many cells are gathered (64^3)
+long long g_tail_cells = 4096;            // closed boxes: levels with at most this many cells form the one-launch tail of the V-cycle
 long long g_split_tiles = 148;            // levels with at least this many 58 x 24 tiles launch wall-free tiles separately
 long long g_overlap_cells = 1LL << 25;     // slab levels with at least this many local cells overlap their halo exchange
 
@@ -65,6 +66,7 @@ struct ny_mg {
     LevelMaps maps[50];
     int fused;                             // use the fused V-cycle legs where a level allows them
     int split_tiles;                       // fused legs: wall-free tiles run the specialised kernel instance
+    int tail;                              // closed boxes: the smallest levels of a V-cycle run in one launch
     int halo_ok;                           // periodic / slab halos of x and b of level 1 are consistent
     int ysync;                             // wall-halo cells of y equal those of x on every level
     int nranks, rank;
@@ -690,6 +692,127 @@ k_prolong_box(double* __restrict__ xf, const double* __restrict__ xc, Box g, Box
 
 #include "ny_mg_vleg.cuh"
 
+// ---- the tail of the V-cycle in ONE launch -------------------------------------------------------
+// Levels of a few thousand cells cost ~20 us per leg as separate launches (pipeline fill, launch and
+// drain dominate) and there are a dozen of them per V-cycle.  For closed boxes (no halo fill between the
+// operators) one CTA runs the whole tail -- smooth, residual + restriction down to the coarsest level, its
+// smoothing, prolongation + smooth back up -- with a block barrier between the operators.  The arrays stay
+// in global memory (a CTA sees its own writes after __syncthreads; no read-only-path loads).  Per-cell
+// arithmetic and operation order are those of k_sweep / k_residual / k_restrict / k_prolong with the
+// analytic box coefficients, hence of the reference (basicoperators.f90:32-60,173-231,300-323,363-400).
+constexpr int TAIL_MAX = 8;
+constexpr int TAIL_THREADS = 1024;
+struct TailLevel { double *x, *y, *b; Box g; };
+struct TailArgs { int n; double omega, cff1; TailLevel lev[TAIL_MAX]; };
+
+// Cells of an ni x nj x nk box dealt to the threads of the CTA in row-major order, without a division per
+// cell: (i, j, k) of the thread's first cell, then steps of TAIL_THREADS cells with carries.
+struct TailIter {
+    int i, j, k, di, dj, dk, ni, nj, left;
+    __device__ __forceinline__ TailIter(int ni_, int nj_, int nk_) : ni(ni_), nj(nj_)
+    {
+        const int t = threadIdx.x, total = ni_ * nj_ * nk_;
+        i = t % ni_; int q = t / ni_; j = q % nj_; k = q / nj_;
+        di = TAIL_THREADS % ni_; q = TAIL_THREADS / ni_; dj = q % nj_; dk = q / nj_;
+        left = t < total ? (total - t + TAIL_THREADS - 1) / TAIL_THREADS : 0;
+    }
+    __device__ __forceinline__ void next()
+    {
+        i += di; if (i >= ni) { i -= ni; j++; }
+        j += dj; if (j >= nj) { j -= nj; k++; }
+        k += dk;
+        left--;
+    }
+};
+
+// one Jacobi sweep src -> dst on the interior widened by `ring` cells (fsmoother3d: ring 1, then ring 0)
+__device__ __forceinline__ void tail_sweep(const double* src, double* dst, const double* b, const Box& g,
+                                           double omega, double cff1, int ring)
+{
+    TailIter it(g.nx + 2 * ring, g.ny + 2 * ring, g.nz - 2 * NH + 2 * ring);
+#pragma unroll 2
+    for (; it.left > 0; it.next()) {
+        const int ai = NH - ring + it.i, aj = NH - ring + it.j, ak = NH - ring + it.k;
+        const long long c = (long long)ak * g.sk + (long long)aj * g.sj + ai;
+        const double s = src[c - 1] + src[c + 1] + src[c - g.sj] + src[c + g.sj] + src[c - g.sk] + src[c + g.sk];
+        const int cnt = cnt_xy(g, ai, aj) + cnt_z(g, ak);
+        const double idiag = cnt > 0 ? 1.0 / (double)cnt : 0.0;
+        dst[c] = cff1 * src[c] + omega * (s - b[c]) * idiag;
+    }
+}
+
+__device__ __forceinline__ double tail_resid(const double* x, const double* b, const Box& g, int ai, int aj, int ak)
+{
+    const long long c = (long long)ak * g.sk + (long long)aj * g.sj + ai;
+    const double s = x[c - 1] + x[c + 1] + x[c - g.sj] + x[c + g.sj] + x[c - g.sk] + x[c + g.sk];
+    const double diag = (double)(cnt_xy(g, ai, aj) + cnt_z(g, ak));
+    return b[c] + diag * x[c] - s;
+}
+
+__global__ void __launch_bounds__(TAIL_THREADS, 1)
+k_vcycle_tail(TailArgs a)
+{
+    const double omega = a.omega, cff1 = a.cff1;
+    auto smooth = [&](const TailLevel& L) {
+        tail_sweep(L.x, L.y, L.b, L.g, omega, cff1, 1);
+        __syncthreads();
+        tail_sweep(L.y, L.x, L.b, L.g, omega, cff1, 0);
+        __syncthreads();
+    };
+    for (int l = 0; l + 1 < a.n; l++) {                 // solvers.f90:41-46
+        const TailLevel& F = a.lev[l];
+        const TailLevel& C = a.lev[l + 1];
+        smooth(F);
+        const Box& g = F.g;
+        const Box& gc = C.g;
+        for (TailIter it(gc.nx, gc.ny, gc.nz - 2 * NH); it.left > 0; it.next()) {
+            const int ic = it.i, jc = it.j, kc = it.k;
+            const int ai = NH + 2 * ic, aj = NH + 2 * jc, ak = NH + 2 * kc;
+            double r = tail_resid(F.x, F.b, g, ai, aj, ak);                     // frestrict_centers3d order
+            r = r + tail_resid(F.x, F.b, g, ai + 1, aj, ak);
+            r = r + tail_resid(F.x, F.b, g, ai, aj + 1, ak);
+            r = r + tail_resid(F.x, F.b, g, ai + 1, aj + 1, ak);
+            r = r + tail_resid(F.x, F.b, g, ai, aj, ak + 1);
+            r = r + tail_resid(F.x, F.b, g, ai + 1, aj, ak + 1);
+            r = r + tail_resid(F.x, F.b, g, ai, aj + 1, ak + 1);
+            r = r + tail_resid(F.x, F.b, g, ai + 1, aj + 1, ak + 1);
+            C.b[(long long)(NH + kc) * gc.sk + (long long)(NH + jc) * gc.sj + (NH + ic)] = 0.5 * r;
+        }
+        const long long nc = gc.sk * gc.nz;
+        for (long long t = threadIdx.x; t < nc; t += TAIL_THREADS) C.x[t] = 0.0;   // operators.f90:209
+        __syncthreads();
+    }
+    smooth(a.lev[a.n - 1]);
+    for (int l = a.n - 2; l >= 0; l--) {                // solvers.f90:51-54
+        const TailLevel& F = a.lev[l];
+        const TailLevel& C = a.lev[l + 1];
+        const Box& g = F.g;
+        const Box& gc = C.g;
+#pragma unroll 2
+        for (TailIter it(g.nx, g.ny, g.nz - 2 * NH); it.left > 0; it.next()) {
+            const int fi = it.i, fj = it.j, fk = it.k;                              // 0-based interior fine cell
+            const int aic = NH + (fi >> 1), ajc = NH + (fj >> 1), akc = NH + (fk >> 1);
+            const int di = (fi & 1) ? 1 : -1, dj = (fj & 1) ? 1 : -1, ako = (fk & 1) ? akc + 1 : akc - 1;
+            const long long ox = di, oy = (long long)dj * gc.sj;
+            const long long cb = (long long)akc * gc.sk + (long long)ajc * gc.sj + aic;
+            const long long co = (long long)ako * gc.sk + (long long)ajc * gc.sj + aic;
+            const double pb = 9 * C.x[cb] + 3 * C.x[cb + ox] + 3 * C.x[cb + oy] + C.x[cb + ox + oy];
+            const double po = 9 * C.x[co] + 3 * C.x[co + ox] + 3 * C.x[co + oy] + C.x[co + ox + oy];
+            const double cf = pcoef_of((int)in_x(gc, aic + di) + (int)in_y(gc, ajc + dj) + (int)in_z(gc, ako));
+            const long long f = (long long)(NH + fk) * g.sk + (long long)(NH + fj) * g.sj + (NH + fi);
+            F.x[f] = F.x[f] + cf * (3 * pb + po);
+        }
+        __syncthreads();
+        smooth(F);
+    }
+    // the fused legs of the finer levels rely on y == x on the wall halos of every level
+    for (int l = 0; l < a.n; l++) {
+        const TailLevel& L = a.lev[l];
+        const long long n = L.g.sk * L.g.nz;
+        for (long long t = threadIdx.x; t < n; t += TAIL_THREADS) L.y[t] = L.x[t];
+    }
+}
+
 inline int ew_blocks(long long n)
 {
     long long b = (n + 255) / 256;
@@ -1230,18 +1353,54 @@ int up_leg(ny_mg* mg, cudaStream_t st, int lev, bool with_norm, int* nparts)
     return fill(mg, st, F, F.x);
 }
 
+// first level (1-based) of the V-cycle tail that k_vcycle_tail runs, or nlevels + 1 when there is none:
+// closed box on analytic coefficients, levels replicated on every rank, at most g_tail_cells cells each
+int tail_first(const ny_mg* mg)
+{
+    const int none = mg->nlevels + 1;
+    if (!mg->box || !mg->fused || !mg->tail || mg->xper || mg->yper || mg->zper) return none;
+    int lt = mg->nlevels;
+    while (lt >= 1) {
+        const Level& L = mg->lev[lt - 1];
+        if (!L.gathered || L.zlo || L.zhi || (long long)L.nx * L.ny * (L.nz - 2 * NH) > g_tail_cells) break;
+        lt--;
+    }
+    lt++;
+    if (lt > mg->nlevels) return none;
+    if (mg->nlevels - lt + 1 > TAIL_MAX) lt = mg->nlevels - TAIL_MAX + 1;
+    return lt;
+}
+
+int vcycle_tail(ny_mg* mg, cudaStream_t st, int lt)
+{
+    TailArgs a;
+    a.n = mg->nlevels - lt + 1;
+    a.omega = mg->omega; a.cff1 = 1.0 - mg->omega;
+    for (int l = 0; l < a.n; l++) {
+        Level& L = mg->lev[lt - 1 + l];
+        a.lev[l].x = L.x; a.lev[l].y = L.y; a.lev[l].b = L.b; a.lev[l].g = box_of(mg, L);
+    }
+    ny_prof_scope ps(mg->ctx, NY_PROF_MG_COARSE, st);
+    k_vcycle_tail<<<1, TAIL_THREADS, 0, st>>>(a);
+    LAUNCH_OK(mg);
+    return NY_OK;
+}
+
 // solvers.f90:35-55.  norm_parts != nullptr: the caller wants sum r^2 of level 1 after the cycle; if the
 // last leg could provide it, *norm_parts = number of partial sums waiting in d_red, else 0.
 int vcycle(ny_mg* mg, cudaStream_t st, int* norm_parts = nullptr)
 {
-    const int lev1 = mg->nlevels - 1;
+    int lev1 = mg->nlevels - 1;
     if (norm_parts) *norm_parts = 0;
+    const int lt = tail_first(mg);
+    if (lt <= mg->nlevels) lev1 = lt - 1;                 // levels lt .. nlevels: one launch
     for (int lev = 1; lev <= lev1; lev++) {
         if (leg_ok(mg, lev)) { TRY(down_leg(mg, st, lev)); continue; }
         TRY(smooth(mg, st, lev));
         TRY(residual_restriction(mg, st, lev));
     }
-    TRY(smooth(mg, st, lev1 + 1));
+    if (lt <= mg->nlevels) TRY(vcycle_tail(mg, st, lt));
+    else TRY(smooth(mg, st, lev1 + 1));
     for (int lev = lev1; lev >= 1; lev--) {
         if (leg_ok(mg, lev)) { TRY(up_leg(mg, st, lev, lev == 1 && norm_parts, norm_parts)); continue; }
         TRY(prolongation(mg, st, lev));
@@ -1407,6 +1566,7 @@ int create(ny_ctx* ctx, ny_comm* comm, int nx, int ny, int nz_global, int topolo
     }
     mg->fused = 1;
     mg->split_tiles = 1;
+    mg->tail = 1;
     mg->halo_ok = 0;
     mg->ysync = 1;                                              // x and y are both zero
     for (int l = 0; l < mg->nlevels; l++) {
@@ -1485,6 +1645,7 @@ extern "C" int ny_mg_create_slab(ny_ctx* ctx, ny_comm* comm, int nx, int ny, int
 extern "C" void ny_mg_set_gather_cells(long long cells) { g_gather_cells = cells; }
 extern "C" void ny_mg_set_overlap_cells(long long cells) { g_overlap_cells = cells; }
 extern "C" void ny_mg_set_split_tiles(long long tiles) { g_split_tiles = tiles; }
+extern "C" void ny_mg_set_tail_cells(long long cells) { g_tail_cells = cells; }
 
 extern "C" int ny_mg_nlevels(ny_mg* mg) { return mg ? mg->nlevels : 0; }
 extern "C" int ny_mg_is_box(ny_mg* mg) { return mg ? mg->box : 0; }
@@ -1504,7 +1665,8 @@ extern "C" int ny_mg_set_fused_legs(ny_mg* mg, int on)
 {
     NY_REQUIRE(mg, "null argument");
     mg->fused = on ? 1 : 0;
-    mg->split_tiles = on == 2 ? 0 : 1;      // 2: fused legs, every tile through the general kernel instance
+    mg->split_tiles = on == 2 ? 0 : 1;      // 2: fused legs, every tile through the general kernel instance,
+    mg->tail = on == 2 ? 0 : 1;             //    and no one-launch tail
     return NY_OK;
 }
 

@@ -112,6 +112,27 @@ def main():
                                                                      lib.ptr(wz), lib.ptr(out[1]), lib.ptr(out[2]), lib.ptr(out[3]), e, st)))
                 print("   sustained vortex force %.3f ms, %s" % (t, c), flush=True)
             del F, out, b, Ux, Uy, Uz, wx, wy, wz, ke
+    if "tail" in a.what:                       # one-launch V-cycle tail: which levels should it take?
+        from nyles_b200.mgfordriver import MG
+        for cells in (0, 512, 4096, 32768):
+            L.ny_mg_set_tail_cells(cells)
+            mg = MG(1, 1, n, n, n, 3, 1)
+            shape = mg.get_arrayshape(1)
+            x = torch.randn(shape, device=dev, dtype=torch.float64, generator=gen)
+            mg.set_array(x, ivar=1)
+            mg.set_array(x * 0.1, ivar=2)
+            del x
+            mg.op("fill", 1)
+            mg.op("vcycle", 1)
+            lib.prof_start()
+            for _ in range(8):
+                mg.op("vcycle", 1)
+            prof = lib.prof_collect()
+            lib.prof_start(0)
+            print("tail_cells=%d: " % cells + ", ".join("%s %.3f ms/%d" % (k, v[0] / 8, v[1] // 8) for k, v in prof.items() if v[1]), flush=True)
+            del mg
+            torch.cuda.empty_cache()
+        L.ny_mg_set_tail_cells(4096)
     if "mg" in a.what:
         from nyles_b200.mgfordriver import MG
         for topo in (1, 6):
