@@ -9,6 +9,8 @@
 #include "ny_common.cuh"
 #include "ny_comm.cuh"
 #include <dlfcn.h>
+#include <cstdlib>
+#include <vector>
 
 namespace {
 
@@ -98,6 +100,9 @@ extern "C" int ny_comm_init(ny_ctx* ctx, int nranks, int rank, const char* id128
     memcpy(id.internal, id128, NCCL_UNIQUE_ID_BYTES);
     ny_comm* c = new ny_comm();
     c->ctx = ctx; c->nranks = nranks; c->rank = rank; c->nccl = nullptr; c->d_red = nullptr;
+    memset(&c->p2p, 0, sizeof(c->p2p));
+    c->p2p.peer_rank[0] = c->p2p.peer_rank[1] = -1;
+    { const char* e = getenv("NY_COMM_P2P"); if (e && e[0] == '0') c->p2p.state = -1; }
     ncclResult_t r = g_nccl.CommInitRank(&c->nccl, nranks, id, rank);
     if (r != ncclSuccess) {
         ny_set_error("ncclCommInitRank(%d of %d) -> %s", rank, nranks, g_nccl.GetErrorString(r));
@@ -120,9 +125,12 @@ extern "C" int ny_comm_init(ny_ctx* ctx, int nranks, int rank, const char* id128
     return NY_OK;
 }
 
+static void p2p_release(ny_comm* c);
+
 extern "C" void ny_comm_free(ny_comm* c)
 {
     if (!c) return;
+    p2p_release(c);
     if (c->nccl && g_nccl.ok) g_nccl.CommDestroy(c->nccl);
     if (c->d_red) cudaFree(c->d_red);
     if (c->xstream) cudaStreamDestroy(c->xstream);
@@ -149,12 +157,231 @@ int ny_comm_allgather_inplace(ny_comm* c, double* d_recv, size_t count_per_rank,
     return NY_OK;
 }
 
+// ---- P2P halo exchange ---------------------------------------------------------------------------
+// ncclSend/ncclRecv moves a 3-plane face at ~90 GB/s per direction (measured, profiles/), a fraction of
+// what NVLink 5 carries, and every group is a rendezvous of both ranks inside NCCL.  Here a rank PUSHES its
+// boundary planes straight into a receive slot in the neighbour's memory (IPC-mapped, plain 16-byte
+// stores over NVLink from a grid of CTAs), raises a flag there once all its stores are globally visible,
+// then waits for the flag the neighbour raises in ITS slot and copies the planes into its halo.
+// Slot reuse needs no acknowledgement: exchanges are issued in the same order on every rank and a rank
+// cannot run more than one exchange ahead of a neighbour whose data it waits for, so with
+// NY_P2P_SLOTS >= 2 (4 here: one exchange may be in flight on the overlap stream as well) a slot is never
+// overwritten before its previous content has been unpacked.
+struct P2PSeg { const double* src; double* dst; unsigned long long count; };
+struct P2PArgs {
+    int nseg;
+    P2PSeg seg[16];
+    unsigned long long* flag[2];      // push: the neighbours' flags to raise; unpack: the local flags to wait for
+    unsigned int* counter;
+    unsigned long long seq;
+};
+
+__device__ __forceinline__ void p2p_copy(const P2PSeg& s, long long first, long long stride)
+{
+    const bool vec = ((((unsigned long long)s.src) | ((unsigned long long)s.dst)) & 15ull) == 0 && (s.count & 1ull) == 0;
+    if (vec) {
+        const double2* a = reinterpret_cast<const double2*>(s.src);
+        double2* b = reinterpret_cast<double2*>(s.dst);
+        const long long n = (long long)(s.count >> 1);
+        long long t = first;
+        for (; t + 3 * stride < n; t += 4 * stride) {          // four independent 16-byte transfers in flight per thread
+            const double2 v0 = a[t], v1 = a[t + stride], v2 = a[t + 2 * stride], v3 = a[t + 3 * stride];
+            b[t] = v0; b[t + stride] = v1; b[t + 2 * stride] = v2; b[t + 3 * stride] = v3;
+        }
+        for (; t < n; t += stride) b[t] = a[t];
+    } else {
+        for (long long t = first; t < (long long)s.count; t += stride) s.dst[t] = s.src[t];
+    }
+}
+
+__global__ void __launch_bounds__(512)
+k_p2p_push(P2PArgs a)
+{
+    const long long first = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+    for (int s = 0; s < a.nseg; s++) p2p_copy(a.seg[s], first, stride);
+    __threadfence_system();                         // my stores are visible to the neighbour's GPU ...
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int done = atomicAdd(a.counter, 1u);
+        if (done == gridDim.x - 1) {                // ... and so are those of every other CTA: raise the flags
+            *a.counter = 0u;
+            __threadfence_system();
+            if (a.flag[0]) *reinterpret_cast<volatile unsigned long long*>(a.flag[0]) = a.seq;
+            if (a.flag[1]) *reinterpret_cast<volatile unsigned long long*>(a.flag[1]) = a.seq;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_p2p_wait_unpack(P2PArgs a)
+{
+    if (threadIdx.x == 0) {
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        for (int d = 0; d < 2; d++) {
+            if (!a.flag[d]) continue;
+            const volatile unsigned long long* f = a.flag[d];
+            while (*f < a.seq) {
+                __nanosleep(200);
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > 60000000000ull) {     // a neighbour died: fail loudly instead of hanging the GPU
+                    printf("libnyles_b200: halo exchange %llu timed out waiting for a slab neighbour\n", a.seq);
+                    __trap();
+                }
+            }
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    const long long first = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+    for (int s = 0; s < a.nseg; s++) p2p_copy(a.seg[s], first, stride);
+}
+
+static void p2p_release(ny_comm* c)
+{
+    ny_p2p& p = c->p2p;
+    if (p.peer[0]) cudaIpcCloseMemHandle(p.peer[0]);
+    if (p.peer[1] && p.peer[1] != p.peer[0]) cudaIpcCloseMemHandle(p.peer[1]);
+    if (p.local) cudaFree(p.local);
+    p.peer[0] = p.peer[1] = nullptr; p.local = nullptr; p.flags = nullptr; p.counters = nullptr;
+    p.slot_bytes = 0;
+    if (p.state == 1) p.state = 0;
+}
+
+// Collective: (re)allocate the receive slots for faces of up to need_bytes per direction and map the
+// neighbours' buffers.  Every rank calls it at the same point with the same size (slabs are equal).
+static int p2p_setup(ny_comm* c, size_t need_bytes, int below, int above)
+{
+    ny_p2p& p = c->p2p;
+    NY_CUDA(cudaDeviceSynchronize());
+    {   // nobody may still be using the old mapping
+        double* z = c->d_red;
+        NY_CUDA(cudaMemset(z, 0, sizeof(double)));
+        NY_NCCL(g_nccl.AllReduce(z, z, 1, ncclDouble, ncclSum, c->nccl, 0));
+        NY_CUDA(cudaDeviceSynchronize());
+    }
+    p2p_release(c);
+    const size_t slot = ((need_bytes + need_bytes / 4 + (1u << 20) - 1) >> 20) << 20;       // 25 % head room, 1 MiB granules
+    const size_t data = 2 * (size_t)NY_P2P_SLOTS * slot, total = data + 4096;
+    int ok = 1;
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof(mine));
+    if (cudaMalloc(&p.local, total) != cudaSuccess) { cudaGetLastError(); p.local = nullptr; ok = 0; }
+    if (ok) {
+        cudaMemset(p.local + data, 0, 4096);
+        if (cudaIpcGetMemHandle(&mine, p.local) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+    }
+    // all-gather the 64-byte handles through NCCL
+    unsigned char* d_h = nullptr;
+    NY_CUDA(cudaMalloc(&d_h, (size_t)c->nranks * sizeof(cudaIpcMemHandle_t)));
+    NY_CUDA(cudaMemcpy(d_h + (size_t)c->rank * sizeof(mine), &mine, sizeof(mine), cudaMemcpyHostToDevice));
+    NY_NCCL(g_nccl.AllGather(d_h + (size_t)c->rank * sizeof(mine), d_h, sizeof(mine), ncclChar, c->nccl, 0));
+    std::vector<cudaIpcMemHandle_t> all(c->nranks);
+    NY_CUDA(cudaMemcpy(all.data(), d_h, (size_t)c->nranks * sizeof(mine), cudaMemcpyDeviceToHost));
+    cudaFree(d_h);
+    const int nb[2] = {below, above};
+    for (int d = 0; d < 2 && ok; d++) {
+        if (nb[d] < 0) continue;
+        if (d == 1 && above == below) { p.peer[1] = p.peer[0]; continue; }
+        void* q = nullptr;
+        if (cudaIpcOpenMemHandle(&q, all[nb[d]], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+        p.peer[d] = static_cast<unsigned char*>(q);
+    }
+    // everybody or nobody
+    double flag = ok ? 0.0 : 1.0;
+    NY_CUDA(cudaMemcpy(c->d_red, &flag, sizeof(double), cudaMemcpyHostToDevice));
+    NY_NCCL(g_nccl.AllReduce(c->d_red, c->d_red, 1, ncclDouble, ncclSum, c->nccl, 0));
+    NY_CUDA(cudaMemcpy(&flag, c->d_red, sizeof(double), cudaMemcpyDeviceToHost));
+    if (flag != 0.0) {
+        p2p_release(c);
+        p.state = -1;
+        if (c->rank == 0)
+            fprintf(stderr, "libnyles_b200: CUDA IPC peer mapping is not available on %d rank(s); halo faces go through "
+                            "ncclSend/ncclRecv\n", (int)flag);
+        return NY_OK;
+    }
+    p.slot_bytes = slot;
+    p.flags = reinterpret_cast<unsigned long long*>(p.local + data);
+    p.counters = reinterpret_cast<unsigned int*>(p.local + data + 2048);
+    p.peer_rank[0] = below; p.peer_rank[1] = above;
+    p.state = 1;
+    return NY_OK;
+}
+
+// faces of nf arrays (plane sizes / interior thicknesses may differ) through the peer slots; returns
+// NY_OK with *done = false when P2P is not available
+static int p2p_exchange(ny_comm* c, double* const* arrays, const size_t* plane, const int* lo, const int* nint, int nf,
+                        int nh, int below, int above, cudaStream_t st, bool* done)
+{
+    ny_p2p& p = c->p2p;
+    *done = false;
+    if (p.state < 0 || nf > 8) return NY_OK;
+    size_t bytes = 0;
+    for (int f = 0; f < nf; f++) bytes += (size_t)nh * plane[f] * sizeof(double);
+    if (p.state == 0 || bytes > p.slot_bytes || p.peer_rank[0] != below || p.peer_rank[1] != above) {
+        // room for four such faces: the first exchange of a run is a single field, vectors and the
+        // multigrid's padded planes follow
+        int r = p2p_setup(c, p.state == 0 ? 4 * bytes : bytes, below, above);
+        if (r != NY_OK) return r;
+        if (p.state != 1) return NY_OK;
+    }
+    const unsigned long long seq = ++p.seq;
+    const int slot = (int)(seq % NY_P2P_SLOTS);
+    const size_t data = 2 * (size_t)NY_P2P_SLOTS * p.slot_bytes;
+    // region 0 of a buffer receives from the rank below, region 1 from the rank above
+    auto slot_of = [&](unsigned char* base, int region) {
+        return reinterpret_cast<double*>(base + ((size_t)region * NY_P2P_SLOTS + slot) * p.slot_bytes);
+    };
+    auto flag_of = [&](unsigned char* base, int region) {
+        return reinterpret_cast<unsigned long long*>(base + data) + region * NY_P2P_SLOTS + slot;
+    };
+    P2PArgs push, pull;
+    memset(&push, 0, sizeof(push));
+    memset(&pull, 0, sizeof(pull));
+    push.seq = pull.seq = seq;
+    push.counter = p.counters + slot;
+    size_t off = 0;
+    for (int f = 0; f < nf; f++) {
+        double* a = arrays[f];
+        const size_t cnt = (size_t)nh * plane[f];
+        if (below >= 0) {      // my lowest interior planes -> the "from above" slot of the rank below
+            push.seg[push.nseg++] = {a + (size_t)lo[f] * plane[f], slot_of(p.peer[0], 1) + off, cnt};
+            pull.seg[pull.nseg++] = {slot_of(p.local, 0) + off, a + (size_t)(lo[f] - nh) * plane[f], cnt};
+        }
+        if (above >= 0) {      // my highest interior planes -> the "from below" slot of the rank above
+            push.seg[push.nseg++] = {a + (size_t)(lo[f] + nint[f] - nh) * plane[f], slot_of(p.peer[1], 0) + off, cnt};
+            pull.seg[pull.nseg++] = {slot_of(p.local, 1) + off, a + (size_t)(lo[f] + nint[f]) * plane[f], cnt};
+        }
+        off += cnt;
+    }
+    if (below >= 0) { push.flag[0] = flag_of(p.peer[0], 1); pull.flag[0] = flag_of(p.local, 0); }
+    if (above >= 0) { push.flag[1] = flag_of(p.peer[1], 0); pull.flag[1] = flag_of(p.local, 1); }
+    const size_t moved = bytes * ((below >= 0) + (above >= 0));
+    const int sms = c->ctx->num_sms > 0 ? c->ctx->num_sms : 148;
+    int nblk = (int)(moved >> 16);                  // one CTA per 64 KiB, 4 .. 2 per SM
+    nblk = nblk < 4 ? 4 : (nblk > 2 * sms ? 2 * sms : nblk);
+    k_p2p_push<<<nblk, 512, 0, st>>>(push);
+    NY_CHECK_LAUNCH(c->ctx);
+    int nblk2 = nblk < 2 * sms ? nblk : 2 * sms;    // every CTA of the unpack polls the arrival flags first
+    k_p2p_wait_unpack<<<nblk2, 256, 0, st>>>(pull);
+    NY_CHECK_LAUNCH(c->ctx);
+    *done = true;
+    return NY_OK;
+}
+
 // Exchange the nh z-faces of nf slab arrays with the ranks below / above (-1: none).
 // Array a: planes of `plane` doubles; lo = index of the first interior plane, nint = interior planes.
 int ny_comm_exchange_z(ny_comm* c, double* const* arrays, int nf, size_t plane, int lo, int nint, int nh,
                        int below, int above, cudaStream_t st)
 {
     if (!c || (below < 0 && above < 0)) return NY_OK;
+    if (nf <= 8) {
+        size_t planes[8]; int los[8], nints[8];
+        for (int f = 0; f < nf; f++) { planes[f] = plane; los[f] = lo; nints[f] = nint; }
+        bool done = false;
+        int r = p2p_exchange(c, arrays, planes, los, nints, nf, nh, below, above, st, &done);
+        if (r != NY_OK || done) return r;
+    }
     const size_t cnt = (size_t)nh * plane;
     NY_NCCL(g_nccl.GroupStart());
     // sends first, then receives in the opposite neighbour order: when below == above (two ranks,
@@ -177,6 +404,12 @@ int ny_comm_exchange_z2(ny_comm* c, double* a0, size_t plane0, int nint0, double
     double* arr[2] = {a0, a1};
     const size_t plane[2] = {plane0, plane1};
     const int nint[2] = {nint0, nint1};
+    {
+        const int los[2] = {nh, nh};
+        bool done = false;
+        int r = p2p_exchange(c, arr, plane, los, nint, 2, nh, below, above, st, &done);
+        if (r != NY_OK || done) return r;
+    }
     NY_NCCL(g_nccl.GroupStart());
     for (int f = 0; f < 2; f++) {                 // same posting order as ny_comm_exchange_z
         double* a = arr[f];

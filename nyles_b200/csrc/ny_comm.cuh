@@ -5,6 +5,21 @@
 #include "../../include/nyles_b200.h"
 
 struct ny_ctx;
+
+// Face exchange over NVLink peer memory (ny_comm.cu, "P2P halo exchange"): every rank owns one buffer of
+// receive slots that its two slab neighbours map through CUDA IPC and write into directly.
+constexpr int NY_P2P_SLOTS = 4;
+struct ny_p2p {
+    int state;                          // 0: not set up yet, 1: in use, -1: unavailable (NCCL send/recv is used)
+    size_t slot_bytes;                  // capacity of one receive slot
+    unsigned char* local;               // [2 directions][NY_P2P_SLOTS][slot_bytes], then the arrival flags
+    unsigned long long* flags;          // local arrival flags [2][NY_P2P_SLOTS] (written by the neighbours)
+    unsigned int* counters;             // [NY_P2P_SLOTS] CTAs of a push that have finished their share
+    unsigned char* peer[2];             // the buffer of the rank below / above as mapped into this process
+    int peer_rank[2];
+    unsigned long long seq;             // exchanges issued so far (identical on every rank)
+};
+
 struct ny_comm {
     ny_ctx* ctx;
     int nranks, rank;
@@ -12,6 +27,7 @@ struct ny_comm {
     double* d_red;            // small device mailbox for host-value reductions
     cudaStream_t xstream;     // high-priority stream for exchanges that overlap interior kernels
     cudaEvent_t ev_ready, ev_done;
+    ny_p2p p2p;
 };
 
 // all return NY_OK or a negative ny_status; no-ops when c is null or has a single rank
