@@ -236,8 +236,16 @@ def family_bytes_per_cell(euler):
 
 # fp64 instructions (DADD+DMUL+DFMA+DSETP) per cell in the interior path of the strict kernels, from cuobjdump -sass
 DP_INSTR_PER_CELL = {"rhs_momentum": 633.0, "rhs_tracer": 321.0}
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` (profiles/), bytes
-TRAFFIC_NCU = {}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch group from `ncu --set full` of this same command
+# (tools/ncu_traffic.py writes the map; the capture itself is never a bench value)
+def traffic_from_ncu():
+    for path in (os.path.join(ROOT, "gpurun_out", "ncu_traffic.json"), os.path.join(ROOT, "profiles", "ncu_traffic.json")):
+        try:
+            with open(path) as f:
+                return json.load(f).get("families", {})
+        except (OSError, ValueError):
+            continue
+    return {}
 
 
 def run_ours(args):
@@ -373,7 +381,7 @@ def run_ours(args):
         t_ms, n = timed[top]
         achieved = fam[top] * local_cells / (t_ms / n * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                    "frac": achieved / peak_gbs, "traffic": TRAFFIC_NCU.get(top), "peak_source": peak_src,
+                    "frac": achieved / peak_gbs, "traffic": traffic_from_ncu().get(top), "peak_source": peak_src,
                     "algorithmic_bytes_per_cell": fam[top], "launch_groups": n, "avg_ms": t_ms / n,
                     "share_of_step": t_ms / ms}
         if top in DP_INSTR_PER_CELL and not args.fast_arith:

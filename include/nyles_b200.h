@@ -235,7 +235,8 @@ int  ny_mg_create_slab(ny_ctx*, ny_comm* comm, int nx, int ny, int nz_global, in
  * (default 64^3); a level whose slab is thinner than 4 planes is gathered in any case */
 void ny_mg_set_gather_cells(long long cells);
 /* slab levels with at least `cells` local cells compute the planes next to their slab neighbours first and
- * exchange them on a second stream while the rest of the slab is computed (default 2^25) */
+ * exchange them on a second stream while the rest of the slab is computed (default: never -- the peer-memory
+ * exchange is cheaper than the split launches; 2^25 is the setting that paid with ncclSend/ncclRecv) */
 void ny_mg_set_overlap_cells(long long cells);
 /* fused legs: levels whose plane holds at least `tiles` 58 x 24 tiles launch the tiles that keep clear of the
  * x / y walls as a separate, wall-free kernel instance (default 148 = one per SM; tests lower it) */

@@ -24,6 +24,7 @@
 // NCCL; once a level is small it is gathered (ncclAllGather) and all coarser levels are solved
 // redundantly on every rank (mirror of mg_setup.f90:275-293 / mod_gluesplit.f90).
 #include "ny_common.cuh"
+#include <cstdlib>
 #include "ny_comm.cuh"
 #include "ny_tma.cuh"
 
@@ -35,7 +36,11 @@ constexpr int MAX_PARTIALS = 1 << 15;
 long long g_gather_cells = 262144;         // levels with at most this many cells are gathered (64^3)
 long long g_tail_cells = 4096;            // closed boxes: levels with at most this many cells form the one-launch tail of the V-cycle
 long long g_split_tiles = 148;            // levels with at least this many 58 x 24 tiles launch wall-free tiles separately
-long long g_overlap_cells = 1LL << 25;     // slab levels with at least this many local cells overlap their halo exchange
+// slab levels with at least this many local cells compute the planes next to their neighbours first and overlap
+// the exchange with the rest.  Off by default: with the peer-memory exchange a 1024^2 x 3 face takes 60 us, less
+// than the two extra pipeline fills of the split launches cost (8 B200, 1024^3: 66.2 ms per step with the
+// overlap, 64.4 without; profiles/r1_p_*).  ny_mg_set_overlap_cells / NY_MG_OVERLAP_CELLS turn it on.
+long long g_overlap_cells = 1LL << 62;
 
 struct Level {
     int nx, ny, nz;                        // nz = local planes including the 2*nh halo planes
@@ -1490,6 +1495,12 @@ int create(ny_ctx* ctx, ny_comm* comm, int nx, int ny, int nz_global, int topolo
     NY_REQUIRE(topology >= NY_TOPO_CLOSED && topology <= NY_TOPO_XYZPERIO, "unknown topology");
     const int P = comm ? comm->nranks : 1, rank = comm ? comm->rank : 0;
     NY_REQUIRE(nz_global % P == 0, "global nz must be a multiple of the number of slabs");
+    {   // experiment switches (bench runs under torchrun): NY_MG_OVERLAP_CELLS, NY_MG_TAIL_CELLS
+        const char* e = getenv("NY_MG_OVERLAP_CELLS");
+        if (e && *e) g_overlap_cells = atoll(e);
+        e = getenv("NY_MG_TAIL_CELLS");
+        if (e && *e) g_tail_cells = atoll(e);
+    }
     ny_mg* mg = new ny_mg();
     memset(mg, 0, sizeof(ny_mg));
     mg->ctx = ctx; mg->comm = P > 1 ? comm : nullptr; mg->nranks = P; mg->rank = rank;
