@@ -265,6 +265,10 @@ int  ny_mg_set_param(ny_mg*, int maxite, double tol, double omega);
 /* set_pyarray / get_pyarray: whole level arrays, device to device */
 int  ny_mg_set_array(ny_mg*, int lev, int ivar, const double* src, void* stream);
 int  ny_mg_get_array(ny_mg*, int lev, int ivar, double* dst, void* stream);
+/* setup_fine_msk + setup_operators (mg_setup.f90:213-223, operators.f90:461-505): rebuild the coarse masks
+ * and Rcoef, Pcoef, diag, idiag of every level after the mask of level 1 was changed with
+ * ny_mg_set_array(.., ivar = 7, ..) -- obstacles, as in core/mgfor/tests.f90:207-212.  Single rank only. */
+int  ny_mg_setup_operators(ny_mg*, void* stream);
 /* solvers.f90:8-33.  Synchronises `stream` once per V-cycle for the stopping test. */
 int  ny_mg_solve(ny_mg*, ny_mg_stats* stats_host, void* stream);
 /* mgfordriver.MG.solve_directly (core/mgfordriver.py:66-78) without the two host copies:

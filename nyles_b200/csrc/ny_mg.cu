@@ -1709,6 +1709,23 @@ extern "C" int ny_mg_set_array(ny_mg* mg, int lev, int ivar, const double* src, 
     return NY_OK;
 }
 
+// setup_fine_msk + setup_operators (mg_setup.f90:213-223, operators.f90:461-505) after the caller changed
+// the mask of level 1 with ny_mg_set_array(.., NY_MG_MSK, ..): coarse masks, Rcoef, Pcoef, diag, idiag of
+// every level are rebuilt by the reference's own algorithm; the analytic box kernels stay in use only if
+// the result is still the default box (it is not, with an obstacle: the generic kernels then run).
+extern "C" int ny_mg_setup_operators(ny_mg* mg, void* stream)
+{
+    NY_REQUIRE(mg, "null argument");
+    NY_REQUIRE(mg->nranks == 1, "user masks need the coefficient arrays, which slab multigrids do not hold");
+    cudaStream_t st = ny_stream(stream);
+    mg->box = 0;
+    int r = setup_operators(mg, st);
+    if (r == NY_OK) r = verify_box(mg, st);
+    mg->ysync = 0;
+    mg->halo_ok = 0;
+    return r;
+}
+
 extern "C" int ny_mg_get_array(ny_mg* mg, int lev, int ivar, double* dst, void* stream)
 {
     NY_REQUIRE(mg && dst && lev >= 1 && lev <= mg->nlevels && var_ptr(mg, lev, ivar), "bad argument");

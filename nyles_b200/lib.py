@@ -92,6 +92,7 @@ _PROTOS = {
     "ny_mg_set_param": ([_P, _I, _D, _D], _I),
     "ny_mg_set_array": ([_P, _I, _I, _P, _P], _I),
     "ny_mg_get_array": ([_P, _I, _I, _P, _P], _I),
+    "ny_mg_setup_operators": ([_P, _P], _I),
     "ny_mg_solve": ([_P, C.POINTER(ny_mg_stats), _P], _I),
     "ny_mg_solve_directly": ([_P, _P, _P, ny_ext, C.POINTER(_I * 3), _D, C.POINTER(ny_mg_stats), _P], _I),
     "ny_mg_project": ([_P] + [_P] * 5 + [_D, _D, _D, ny_ext, C.POINTER(_I * 3), _D, C.POINTER(ny_mg_stats), _P], _I),

@@ -138,6 +138,13 @@ class MG(object):
             _tensor(array).copy_(out)
         return array
 
+    def set_mask(self, msk):
+        """Obstacles: msk (padded multigrid shape of level 1, 1 = fluid, 0 = solid) replaces the default mask;
+        the coarse masks and the coefficients of every level are rebuilt by the reference's own setup
+        (mgfor/tests.f90:207-212: write oper(1)%msk, setup_fine_msk, setup_operators)."""
+        self.set_array(msk, ivar=7)
+        lib.check(self.L.ny_mg_setup_operators(self.mg, lib.stream()))
+
     def is_box(self):
         return bool(self.L.ny_mg_is_box(self.mg))
 

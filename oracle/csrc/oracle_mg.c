@@ -322,6 +322,15 @@ void orc_mg_setup_operators(orc_mg *mg)
     for (lev = 1; lev <= mg->nlevels; lev++) compute_diag(mg, lev);
 }
 
+/* ---- mg_setup.f90:213-223 setup_fine_msk: halo-fill the finest mask through y ---- */
+void orc_mg_setup_fine_msk(orc_mg *mg)
+{
+    orc_level *L = &mg->lev[0];
+    for (size_t i = 0; i < L->n; i++) L->y[i] = L->msk[i];
+    fill(mg, L, L->y);
+    for (size_t i = 0; i < L->n; i++) L->msk[i] = (int)L->y[i];
+}
+
 void orc_mg_free(orc_mg *mg)
 {
     if (!mg) return;
@@ -359,13 +368,7 @@ orc_mg *orc_mg_create(int nx, int ny, int nz, int topology)
             for (int j = 1; j <= L->ny; j++)
                 for (int i = 1; i <= L->nx; i++) L->msk[IX(L, nh, i, j, k)] = 1;
     }
-    /* setup_fine_msk :213-223: halo-fill the finest mask through y */
-    {
-        orc_level *L = &mg->lev[0];
-        for (size_t i = 0; i < L->n; i++) L->y[i] = L->msk[i];
-        fill(mg, L, L->y);
-        for (size_t i = 0; i < L->n; i++) L->msk[i] = (int)L->y[i];
-    }
+    orc_mg_setup_fine_msk(mg);
     orc_mg_setup_operators(mg);
     return mg;
 }

@@ -187,6 +187,12 @@ class OracleMG(object):
         assert self.L.orc_mg_get_array(self.mg, lev, ivar, _p(array)) == 0
         return array
 
+    def set_mask(self, msk):
+        """mgfor/tests.f90:207-212: a user mask at level 1, then setup_fine_msk + setup_operators."""
+        self.set_array(msk, ivar=7)
+        self.L.orc_mg_setup_fine_msk(self.mg)
+        self.L.orc_mg_setup_operators(self.mg)
+
     def _solve(self):
         self.L.orc_mg_solve(self.mg)
         nite, res, normb = C.c_int(), C.c_double(), C.c_double()

@@ -224,3 +224,39 @@ def test_fused_legs_equal_single_operator_kernels(grid, split):
         np.testing.assert_allclose(fused.stats["res"], plain.stats["res"], rtol=1e-11, atol=0)
         assert torch.equal(xf, xp)
     lib.load().ny_mg_set_split_tiles(148)
+
+
+@pytest.mark.parametrize("grid", [(32, 16, 16, 1), (16, 16, 16, 6), (16, 32, 8, 5)])
+def test_obstacle_mask_rebuilds_the_operators(grid):
+    """a user mask at level 1 (set_pyarray ivar=7, mgfor/tests.f90:207-212) followed by
+    setup_fine_msk + setup_operators.  Coarse masks and every coefficient array must equal the oracle's bit for
+    bit, the analytic box kernels must step aside, and V-cycles / solves on the masked domain must match."""
+    nx, ny, nz, topo = grid
+    g, o = make(*grid)
+    assert g.is_box()
+    msk = o.get_array(ivar=7)
+    msk[3 + nz // 4:3 + nz // 2, 3 + ny // 4:3 + ny // 2 + 1, 3 + nx // 2:3 + nx // 2 + 5] = 0.0     # a block
+    msk[3:3 + 2, 3 + ny - 3:3 + ny, 3:3 + 3] = 0.0                                                   # a corner step
+    g.set_mask(msk)
+    o.set_mask(msk)
+    assert not g.is_box()
+    for lev in range(1, g.nlevels + 1):
+        for name in ("msk", "diag", "idiag", "Rcoef", "Pcoef"):
+            assert np.array_equal(host(g.get_array(ivar=IVARS[name], lev=lev)), o.get_array(ivar=IVARS[name], lev=lev)), \
+                "level %d %s" % (lev, name)
+    assert host(g.get_array(ivar=5, lev=1))[3 + nz // 4, 3 + ny // 4, 3 + nx // 2] == 0.0       # solid: no equation
+    rng = np.random.default_rng(8)
+    shape = g.get_arrayshape(1)
+    fluid = o.get_array(ivar=7)[3:-3, 3:-3, 3:-3] > 0
+    for rep in range(2):
+        b = np.zeros(shape)
+        inner = rng.standard_normal((nz, ny, nx)) * fluid
+        inner[fluid] -= inner[fluid].mean()                       # compatible right-hand side on the fluid cells
+        b[3:-3, 3:-3, 3:-3] = inner
+        xg, xo = np.zeros(shape), np.zeros(shape)
+        g.solve(xg, b, fill_halo=True)
+        o.solve(xo, b)
+        assert g.stats["nite"] == o.nite and o.nite >= 1
+        np.testing.assert_allclose(g.stats["res"], o.reshist, rtol=1e-10, atol=0)
+        assert np.array_equal(xg, xo)
+        assert np.all(xg[3:-3, 3:-3, 3:-3][~fluid] == 0.0)        # nothing is ever written inside the obstacle

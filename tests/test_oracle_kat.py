@@ -228,3 +228,28 @@ def test_mg_point_source_converges():
 def test_mg_rejects_grids_it_cannot_coarsen():
     with pytest.raises(ValueError):
         OracleMG(1, 1, 12, 12, 8, 3, topology=1)      # 12 -> 6 -> 3 -> 1: never reaches nx == 2 or ny == 2
+
+
+def test_mg_obstacle_mask():
+    """A solid block inside the box (mgfor/tests.f90:207-212): no equation inside it (diag = 0), one neighbour
+    fewer next to it, coarse masks follow, and the masked problem still converges."""
+    n = 16
+    mg = OracleMG(1, 1, n, n, n, 3, topology=1)
+    msk = mg.get_array(ivar=7)
+    msk[3 + 4:3 + 8, 3 + 4:3 + 8, 3 + 6:3 + 10] = 0.0
+    mg.set_mask(msk)
+    diag = mg.get_array(ivar=5)
+    assert np.all(diag[3 + 4:3 + 8, 3 + 4:3 + 8, 3 + 6:3 + 10] == 0.0)
+    assert diag[3 + 5, 3 + 5, 3 + 5] == 5.0 and diag[3 + 5, 3 + 5, 3 + 4] == 6.0      # next to the block / one further
+    m2 = mg.get_array(ivar=7, lev=2)
+    assert m2[3 + 2, 3 + 2, 3 + 3] == 0.0 and m2.sum() == 8 ** 3 - 2 * 2 * 2
+    fluid = msk[3:-3, 3:-3, 3:-3] > 0
+    rng = np.random.default_rng(2)
+    inner = rng.standard_normal((n, n, n)) * fluid
+    inner[fluid] -= inner[fluid].mean()
+    b = np.zeros(mg.shape)
+    b[3:-3, 3:-3, 3:-3] = inner
+    x = np.zeros(mg.shape)
+    mg.solve(x, b)
+    assert 1 <= mg.nite <= 20 and mg.res < 1e-6
+    assert np.all(x[3:-3, 3:-3, 3:-3][~fluid] == 0.0)
