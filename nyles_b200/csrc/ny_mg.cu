@@ -1734,9 +1734,20 @@ extern "C" int ny_mg_get_array(ny_mg* mg, int lev, int ivar, double* dst, void* 
     return NY_OK;
 }
 
+// The stopping test reads two scalars per V-cycle.  They are stored into the pinned mailbox by a kernel
+// (pinned host memory is device-addressable under unified addressing) instead of a cudaMemcpyAsync: a copy
+// would queue in the device-to-host copy engine behind any bulk download that overlaps the solve
+// (Nyles.step_host returns finished fields while the last projection runs) and stall every V-cycle.
+__global__ void k_store_scalars(const double* __restrict__ src, double* dst_host, int n)
+{
+    if ((int)threadIdx.x < n) dst_host[threadIdx.x] = src[threadIdx.x];
+    __threadfence_system();
+}
+
 static int read_scalars(ny_mg* mg, cudaStream_t st, int n)
 {
-    NY_CUDA(cudaMemcpyAsync(mg->ctx->h_pinned, mg->d_red + MAX_PARTIALS, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    k_store_scalars<<<1, 32, 0, st>>>(mg->d_red + MAX_PARTIALS, mg->ctx->h_pinned, n);
+    NY_CHECK_LAUNCH(mg->ctx);
     NY_CUDA(cudaStreamSynchronize(st));
     return NY_OK;
 }

@@ -26,6 +26,14 @@ class Timescheme(object):
             self.ds1 = state.duplicate_prognostic_variables()
             self.ds2 = state.duplicate_prognostic_variables()
         self.L = lib.load()
+        # optional callable(state), run after the last update of the prognostic fields of a step and before the
+        # diagnose_var that ends it (Nyles.step_host starts the download of the finished fields there)
+        self.before_last_diagnose = None
+
+    def _last_diagnose(self, state):
+        if self.before_last_diagnose is not None:
+            self.before_last_diagnose(state)
+        self.diagnose_var(state)
 
     def set(self, rhs, diagnose_var, rhs_update_u=None, rhs_step=None, tracer_rhs=None):
         self.rhs = rhs
@@ -67,7 +75,7 @@ class Timescheme(object):
         self.rhs(state, t, self.dstate, last=True)
         for s, ds in self._each(state, self.dstate):
             lib.check(self.L.ny_ts_axpy(lib.context(s.device), lib.ptr(s), lib.ptr(ds), dt, s.numel(), lib.stream()))
-        self.diagnose_var(state)
+        self._last_diagnose(state)
 
     # ----------------------------------------
     def LFAM3(self, state, t, dt, **kwargs):
@@ -78,7 +86,7 @@ class Timescheme(object):
                 L.ny_ts_lfam3_first(lib.context(s.device), lib.ptr(s), lib.ptr(ds), lib.ptr(sb), lib.ptr(sn), dt,
                                     s.numel(), lib.stream())))
             self.first = False
-            self.diagnose_var(state)
+            self._last_diagnose(state)
             return
         self._rhs_and_update(state, t, 2, dt, False, three, lambda s, ds, sb, sn: lib.check(     # predictor
             L.ny_ts_lfam3_pred(lib.context(s.device), lib.ptr(s), lib.ptr(ds), lib.ptr(sb), lib.ptr(sn), dt,
@@ -88,7 +96,7 @@ class Timescheme(object):
                              lambda s, ds, sn: lib.check(
             L.ny_ts_lfam3_corr(lib.context(s.device), lib.ptr(s), lib.ptr(ds), lib.ptr(sn), dt, s.numel(),
                                lib.stream())))
-        self.diagnose_var(state)
+        self._last_diagnose(state)
 
     # ----------------------------------------
     def RK3_SSP(self, state, t, dt, **kwargs):
@@ -106,4 +114,4 @@ class Timescheme(object):
         for s, d0, d1, d2 in self._each(state, self.ds0, self.ds1, self.ds2):
             lib.check(L.ny_ts_rk3_stage3(lib.context(s.device), lib.ptr(s), lib.ptr(d0), lib.ptr(d1), lib.ptr(d2),
                                          dt, s.numel(), lib.stream()))
-        self.diagnose_var(state)
+        self._last_diagnose(state)
