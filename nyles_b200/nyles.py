@@ -14,6 +14,7 @@ from . import lib
 from . import model_les
 from . import model_les_euler
 from . import mpitools
+from .online_diag import VFwork
 from . import nylesIO
 from . import timing
 from . import topology as topo
@@ -68,6 +69,7 @@ class Nyles(object):
         self.dt_max = param["dt_max"]
         self.plotting = None
         self.gridcellpersubdom = param["nx"] * param["ny"] * param["nz"]
+        self.diag = VFwork(self.model, self.grid)                      # core/nyles.py:102
 
     def run(self, max_steps=None, quiet=False):
         t, n = 0.0, 0
@@ -86,6 +88,11 @@ class Nyles(object):
             blowup = self.model.forward(t, dt)
             t += dt
             n += 1
+            if self.IO.enabled and t >= self.IO.t_next_hist and self.model.nonlinear:      # core/nyles.py:167-171
+                self.diag.compute()
+                Kdiss = mpitools.global_sum(self.diag.worksum)
+                if self.myrank == 0 and not quiet:
+                    print("\nKdiss = {}".format(Kdiss))
             stop = self.IO.write(self.model.state, t, n)
             if self.myrank == 0 and not quiet:
                 realtime = time()

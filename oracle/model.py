@@ -278,6 +278,22 @@ def compute_p(K, mg, state, grid):
 
 
 # ---------------------------------------------------------------- model + time scheme
+def vf_work(K, state, dstate, work, domainindices):
+    """core/online_diag.py:4-35: work[...] = sum_d centred(U_d * du_d / 2) with du the vortex force alone;
+    returns the interior sum."""
+    for d in "ijk":
+        dstate.u[d].view("i")[...] = 0.0
+    vortex_force(K, state, dstate)
+    for d in "ijk":
+        u1, u2, res = state.U[d].view(d), dstate.u[d].view(d), work.view(d)
+        if d == "i":
+            res[:] = 0.0
+        product = u1 * u2 * 0.5
+        res[:, :, 1:] += product[:, :, 1:] + product[:, :, :-1]
+    k0, k1, j0, j1, i0, i1 = domainindices
+    return work.view("i")[k0:k1, j0:j1, i0:i1].sum()
+
+
 class LES(object):
     """model_les.LES / model_les_euler.LES (modelname 'LES' | 'Euler3d' | 'linear')."""
 

@@ -210,3 +210,63 @@ def test_views_survive_the_buffer_rotation_and_passive_tracers_follow():
     for d in "ijk":
         assert relerr(st.u[d].tensor.cpu().numpy(), o.state.u[d].data) <= 1e-11
     assert float(st.u["i"].tensor.abs().max()) > 0
+
+
+def test_vortex_force_work_diagnostic():
+    """core/online_diag.py VFwork after a few steps of a developing flow: the work field equals the oracle's
+    bit for bit (same elementwise order), its interior sum to round-off."""
+    kw = dict(nx=32, ny=16, nz=16, geometry="closed", Lx=4.0, Ly=2.0, Lz=2.0, cfl=0.8, dt_max=0.05)
+    o = M.LES(M.make_param(**kw))
+    ny = make_nyles(kw)
+    rng = np.random.default_rng(5)
+    ic = np.tanh((o.grid.x_b - 2.0 + 0.1 * rng.standard_normal(o.grid.x_b.shape)) / (2 * o.grid.dx))
+    o.state.b.view("i")[:] = ic
+    ny.model.state.b.view("i")[:] = ic
+    o.diagnose_var(o.state)
+    ny.model.diagnose_var(ny.model.state)
+    t = 0.0
+    for n in range(4):
+        dt = o.compute_dt()
+        o.forward(t, dt)
+        ny.model.forward(t, dt)
+        t += dt
+    ds = o.state.duplicate_prognostic_variables()
+    want = M.vf_work(o.K, o.state, ds, o.state.work, o.state.b.domainindices)
+    ny.diag.compute()
+    got = ny.model.state.work.tensor.cpu().numpy()
+    assert np.array_equal(got, o.state.work.data)
+    assert np.abs(o.state.work.data).max() > 0
+    assert abs(ny.diag.worksum - want) <= 1e-12 * np.abs(o.state.work.data).sum()
+
+
+def test_run_writes_the_history_file(tmp_path, capsys):
+    """Nyles.run() end to end (core/nyles.py:119-225): time loop, history cadence, the VFwork print, the final
+    snapshot, the netCDF file in the reference's layout with the model's fields in it."""
+    from scipy.io import netcdf_file
+    from nyles_b200 import parameters, nyles
+    parameters.InextensibleDict.unfreeze()
+    up = parameters.UserParameters()
+    up.model["geometry"] = "closed"
+    up.model["Lx"], up.model["Ly"], up.model["Lz"] = 4.0, 2.0, 2.0
+    up.discretization["global_nx"], up.discretization["global_ny"], up.discretization["global_nz"] = 32, 16, 16
+    up.time["cfl"], up.time["dt_max"], up.time["tend"] = 0.8, 0.05, 0.22
+    up.IO["datadir"], up.IO["expname"], up.IO["timestep_history"] = str(tmp_path), "run_test", 0.1
+    up.IO["variables_in_history"] = "p+p"
+    ny = nyles.Nyles(up)
+    rng = np.random.default_rng(1)
+    x = np.asarray(ny.grid.x_b.view("i"))
+    ny.model.state.b.view("i")[:] = np.tanh((x - 2.0 + 0.1 * rng.standard_normal(x.shape)) / (2 * ny.grid.dx))
+    ny.run()
+    out = capsys.readouterr().out
+    assert "Kdiss = " in out and "Job completed as expected" in out
+    assert ny.n == 5 and abs(ny.t - 0.25) < 1e-12          # dt = dt_max while the flow is slow
+    f = netcdf_file(ny.IO.hist_path, "r", mmap=False)
+    f.__dict__["mode"] = "r"
+    assert list(f.variables["n"][:]) == [0, 2, 4, 5]        # t = 0, 0.1, 0.2 and the final state
+    assert np.allclose(f.variables["t"][:], [0.0, 0.1, 0.2, 0.25])
+    assert np.array_equal(f.variables["b"][3], ny.model.state.b.tensor.cpu().numpy())
+    assert np.array_equal(f.variables["u"][3], ny.model.state.u["i"].tensor.cpu().numpy())
+    assert np.array_equal(f.variables["p"][3], ny.model.state.p.tensor.cpu().numpy())
+    assert f.global_nx == 32 and f.geometry == b"closed"
+    f.close()
+    assert os.path.isfile(os.path.join(ny.IO.output_directory, "param.pkl"))
