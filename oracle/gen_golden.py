@@ -151,6 +151,10 @@ CASES = {
     "les_closed_rk3": ("LES", "closed", (8, 16, 8), (1.0, 2.0, 1.0), {"timestepping": "RK3_SSP"}, 2),
     "les_closed_ef_diff": ("LES", "closed", (8, 8, 8), (1.0, 1.0, 1.0),
                            {"timestepping": "EF", "diff_coef": {"u": 1e-3, "b": 2e-3}}, 3),
+    # modelname "linear": LES(linear=True) -- no vortex force, no vorticity / kinetic energy (nyles.py:93-100)
+    "linear_closed": ("linear", "closed", (8, 8, 16), (1.0, 1.0, 2.0), {"uamp": 0.5}, 3),
+    # one passive tracer next to the buoyancy (model_les.py:36-43, tracer.py:44-72)
+    "les_closed_tracer": ("LES", "closed", (16, 8, 8), (2.0, 1.0, 1.0), {"n_tracers": 1, "uamp": 1.0}, 3),
 }
 
 
@@ -194,13 +198,23 @@ def run_case(name):
     loc = topo.rank2loc(0, procs)
     param.update(procs=procs, myrank=0, loc=loc, neighbours=topo.get_neighbours(loc, procs))
     grid = grid_module.Grid(param)
-    model = (model_les_euler.LES if modelname == "Euler3d" else model_les.LES)(param, grid)
+    if modelname == "Euler3d":
+        model = model_les_euler.LES(param, grid)
+    elif modelname == "linear":
+        model = model_les.LES(param, grid, linear=True)
+    else:
+        model = model_les.LES(param, grid)
     st = model.state
+    tracers = ["t%d" % i for i in range(param["n_tracers"])] if modelname != "Euler3d" else []
     shape = st.b.view("i").shape
     ic = initial_fields(name, shape, uamp=extra.get("uamp", 1e-3))
     st.b.view("i")[:] = ic["b"] if modelname != "Euler3d" else 0.0
     for d in "ijk":
         st.u[d].view("i")[:] = ic["u_" + d]
+    for n, nick in enumerate(tracers):
+        zz, yy, xx = np.meshgrid(*[np.linspace(0, 1, m) for m in shape], indexing="ij")
+        ic[nick] = np.cos((2 + n) * np.pi * xx) * np.sin(np.pi * zz) + 0.2 * yy
+        st.get(nick).view("i")[:] = ic[nick]
 
     fake = types.SimpleNamespace(auto_dt=True, model=model, cfl=param["cfl"], dt_max=param["dt_max"], dt0=param["dt"])
     out = {"shape": np.array(shape), "nsteps": nsteps}
@@ -208,7 +222,7 @@ def run_case(name):
         out["ic_" + k] = v
 
     def snap(tag):
-        for sname in ("b", "p", "ke", "div"):
+        for sname in ["b", "p", "ke", "div"] + tracers:
             out["%s_%s" % (tag, sname)] = getattr(st, sname).view("i").copy()
         for vname in ("u", "U", "vor"):
             for d in "ijk":
@@ -220,6 +234,8 @@ def run_case(name):
     ds = st.duplicate_prognostic_variables()
     model.rhs(st, 0.0, ds, last=True)
     out["rhs0_b"] = ds.b.view("i").copy()
+    for nick in tracers:
+        out["rhs0_" + nick] = ds.get(nick).view("i").copy()
     for d in "ijk":
         out["rhs0_u_" + d] = ds.u[d].view("i").copy()
 

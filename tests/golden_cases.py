@@ -13,10 +13,17 @@ CASES = {
     "les_closed_rk3": ("LES", "closed", (8, 16, 8), (1.0, 2.0, 1.0), {"timestepping": "RK3_SSP"}, 2),
     "les_closed_ef_diff": ("LES", "closed", (8, 8, 8), (1.0, 1.0, 1.0),
                            {"timestepping": "EF", "diff_coef": {"u": 1e-3, "b": 2e-3}}, 3),
+    "linear_closed": ("linear", "closed", (8, 8, 16), (1.0, 1.0, 2.0), {}, 3),
+    "les_closed_tracer": ("LES", "closed", (16, 8, 8), (2.0, 1.0, 1.0), {"n_tracers": 1}, 3),
 }
 
 SCALARS = ("b", "p", "ke", "div")
 VECTORS = ("u", "U", "vor")
+
+
+def tracers(name):
+    """Nicknames of the passive tracers of a case."""
+    return ["t%d" % i for i in range(CASES[name][4].get("n_tracers", 0))]
 
 
 def flat_param(name):

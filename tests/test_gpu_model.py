@@ -12,7 +12,7 @@ import pytest
 import torch
 
 from oracle import model as M
-from golden_cases import CASES, SCALARS, VECTORS, flat_param
+from golden_cases import CASES, SCALARS, VECTORS, flat_param, tracers
 
 pytestmark = pytest.mark.gpu
 
@@ -45,12 +45,14 @@ def relerr(a, b):
     return d / s if s > 0 else d
 
 
-def set_ic(ny, g, euler):
+def set_ic(ny, g, euler, extra=()):
     st = ny.model.state
     if not euler:
         st.b.view("i")[:] = g["ic_b"]
     for d in "ijk":
         st.u[d].view("i")[:] = g["ic_u_" + d]
+    for nick in extra:
+        st.get(nick).view("i")[:] = g["ic_" + nick]
 
 
 @pytest.mark.parametrize("fused", [True, False])
@@ -61,12 +63,12 @@ def test_against_reference_driver_fixtures(name, fused, golden_dir):
     ny = make_nyles(kw)
     ny.model.fused = fused
     euler = kw["modelname"] == "Euler3d"
-    set_ic(ny, g, euler)
+    set_ic(ny, g, euler, tracers(name))
     st = ny.model.state
     ny.model.diagnose_var(st)
 
     def compare(tag, tol):
-        for s in SCALARS:
+        for s in tuple(SCALARS) + tuple(tracers(name)):
             a = getattr(st, s).tensor.cpu().numpy()
             assert relerr(a, g["%s_%s" % (tag, s)]) <= tol, "%s %s_%s" % (name, tag, s)
         for v in VECTORS:
@@ -78,6 +80,8 @@ def test_against_reference_driver_fixtures(name, fused, golden_dir):
     ds = st.duplicate_prognostic_variables()
     ny.model.rhs(st, 0.0, ds, last=True)
     assert relerr(ds.b.tensor.cpu().numpy(), g["rhs0_b"]) <= 1e-12
+    for nick in tracers(name):
+        assert relerr(ds.get(nick).tensor.cpu().numpy(), g["rhs0_" + nick]) <= 1e-12
     for d in "ijk":
         assert relerr(ds.u[d].tensor.cpu().numpy(), g["rhs0_u_" + d]) <= 1e-12
     t = 0.0

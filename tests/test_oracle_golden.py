@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from oracle import model as M
-from golden_cases import CASES, SCALARS, VECTORS, flat_param
+from golden_cases import CASES, SCALARS, VECTORS, flat_param, tracers
 
 
 def _run_oracle(name, g):
@@ -18,11 +18,13 @@ def _run_oracle(name, g):
         st.b.view("i")[:] = g["ic_b"]
     for d in "ijk":
         st.u[d].view("i")[:] = g["ic_u_" + d]
+    for nick in tracers(name):
+        st.get(nick).view("i")[:] = g["ic_" + nick]
     m.diagnose_var(st)
     out = {}
 
     def snap(tag):
-        for s in SCALARS:
+        for s in tuple(SCALARS) + tuple(tracers(name)):
             out["%s_%s" % (tag, s)] = getattr(st, s).view("i").copy()
         for v in VECTORS:
             for d in "ijk":
@@ -32,6 +34,8 @@ def _run_oracle(name, g):
     ds = st.duplicate_prognostic_variables()
     m.rhs(st, 0.0, ds, last=True)
     out["rhs0_b"] = ds.b.view("i").copy()
+    for nick in tracers(name):
+        out["rhs0_" + nick] = ds.get(nick).view("i").copy()
     for d in "ijk":
         out["rhs0_u_" + d] = ds.u[d].view("i").copy()
     t, dts = 0.0, []
