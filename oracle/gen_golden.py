@@ -155,6 +155,9 @@ CASES = {
     "linear_closed": ("linear", "closed", (8, 8, 16), (1.0, 1.0, 2.0), {"uamp": 0.5}, 3),
     # one passive tracer next to the buoyancy (model_les.py:36-43, tracer.py:44-72)
     "les_closed_tracer": ("LES", "closed", (16, 8, 8), (2.0, 1.0, 1.0), {"n_tracers": 1, "uamp": 1.0}, 3),
+    # rotating frame + a user forcing object, as experiments/forced_convection/forced_plume.py sets them up
+    "les_closed_forced_rot": ("LES", "closed", (8, 8, 16), (1.0, 1.0, 2.0),
+                              {"forced": True, "rotating": True, "coriolis": 1.0, "forcing": "plume", "uamp": 0.5}, 3),
 }
 
 
@@ -204,6 +207,10 @@ def run_case(name):
         model = model_les.LES(param, grid, linear=True)
     else:
         model = model_les.LES(param, grid)
+    if extra.get("forcing") == "plume":
+        sys.path.insert(0, os.path.join(os.path.dirname(HERE), "tests"))
+        from golden_cases import PlumeForcing
+        model.forcing = PlumeForcing(param, grid)          # "the user must attach the forcing to the model"
     st = model.state
     tracers = ["t%d" % i for i in range(param["n_tracers"])] if modelname != "Euler3d" else []
     shape = st.b.view("i").shape

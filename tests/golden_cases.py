@@ -15,6 +15,9 @@ CASES = {
                            {"timestepping": "EF", "diff_coef": {"u": 1e-3, "b": 2e-3}}, 3),
     "linear_closed": ("linear", "closed", (8, 8, 16), (1.0, 1.0, 2.0), {}, 3),
     "les_closed_tracer": ("LES", "closed", (16, 8, 8), (2.0, 1.0, 1.0), {"n_tracers": 1}, 3),
+    # the plume set-up of experiments/forced_convection/forced_plume.py: rotating frame + user forcing object
+    "les_closed_forced_rot": ("LES", "closed", (8, 8, 16), (1.0, 1.0, 2.0),
+                              {"forced": True, "rotating": True, "coriolis": 1.0, "forcing": "plume"}, 3),
 }
 
 SCALARS = ("b", "p", "ke", "div")
@@ -29,5 +32,30 @@ def tracers(name):
 def flat_param(name):
     modelname, geometry, (nx, ny, nz), (Lx, Ly, Lz), extra, nsteps = CASES[name]
     kw = dict(modelname=modelname, cfl=0.8, dt_max=0.05)
-    kw.update(extra)
+    kw.update({k: v for k, v in extra.items() if k != "forcing"})
     return dict(nx=nx, ny=ny, nz=nz, geometry=geometry, Lx=Lx, Ly=Ly, Lz=Lz, **kw), nsteps
+
+
+class PlumeForcing(object):
+    """The user forcing object of experiments/forced_convection/forced_plume.py:68-80 (a Gaussian column heat
+    source added to db), written against the reference's grid / state API so that the same class drives the
+    reference's drivers (oracle/gen_golden.py), the oracle and nyles_b200."""
+
+    def __init__(self, param, grid):
+        def coord(a):              # Scalar-like in the reference and in nyles_b200, a plain (k,j,i) array in the oracle
+            return a if isinstance(a, np.ndarray) else np.asarray(a.view("i"))
+        x = coord(grid.x_b) / param["Lx"] - 0.5
+        y = coord(grid.y_b) / param["Ly"] - 0.5
+        z = coord(grid.z_b) / param["Lz"]
+        d = np.sqrt(x ** 2 + y ** 2)
+        msk = 0.5 * (1. - np.tanh(d / 0.1))
+        self.Q = 1e-1 * np.exp(-z / 0.02) * msk
+
+    def add(self, state, dstate, time):
+        db = dstate.b.view("i")
+        db += self.Q
+
+
+def forcing_of(name, param, grid):
+    kind = CASES[name][4].get("forcing")
+    return PlumeForcing(param, grid) if kind == "plume" else None

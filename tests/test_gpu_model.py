@@ -12,7 +12,7 @@ import pytest
 import torch
 
 from oracle import model as M
-from golden_cases import CASES, SCALARS, VECTORS, flat_param, tracers
+from golden_cases import CASES, SCALARS, VECTORS, flat_param, forcing_of, tracers
 
 pytestmark = pytest.mark.gpu
 
@@ -62,6 +62,7 @@ def test_against_reference_driver_fixtures(name, fused, golden_dir):
     kw, nsteps = flat_param(name)
     ny = make_nyles(kw)
     ny.model.fused = fused
+    ny.model.forcing = forcing_of(name, ny.param, ny.grid)
     euler = kw["modelname"] == "Euler3d"
     set_ic(ny, g, euler, tracers(name))
     st = ny.model.state

@@ -6,13 +6,14 @@ import numpy as np
 import pytest
 
 from oracle import model as M
-from golden_cases import CASES, SCALARS, VECTORS, flat_param, tracers
+from golden_cases import CASES, SCALARS, VECTORS, flat_param, forcing_of, tracers
 
 
 def _run_oracle(name, g):
     kw, nsteps = flat_param(name)
     p = M.make_param(**kw)
     m = M.LES(p)
+    m.forcing = forcing_of(name, p, m.grid)
     st = m.state
     if kw["modelname"] != "Euler3d":
         st.b.view("i")[:] = g["ic_b"]
