@@ -253,3 +253,301 @@ def test_mg_obstacle_mask():
     mg.solve(x, b)
     assert 1 <= mg.nite <= 20 and mg.res < 1e-6
     assert np.all(x[3:-3, 3:-3, 3:-3][~fluid] == 0.0)
+
+
+# ------------------------------------------------------------------ a second, independent restatement
+def _weno3_py(qm, q0, qp):
+    """core/weno.f90:1-22 written again from the source, in Python floats (IEEE double, no contraction);
+    un-suffixed literals are REAL(4)."""
+    f = np.float32
+    eps = float(f(1e-14))
+    qi1 = (-qm + 3 * q0) * 0.5
+    qi2 = (q0 + qp) * 0.5
+    d1, d2 = q0 - qm, qp - q0
+    beta1, beta2 = d1 * d1, d2 * d2
+    tau = abs(beta2 - beta1)
+    w1 = 1. + tau / (beta1 + eps)
+    w2 = (1. + tau / (beta2 + eps)) * 2
+    return (w1 * qi1 + w2 * qi2) / (w1 + w2)
+
+
+def _weno5_py(qmm, qm, q0, qp, qpp):
+    """core/weno.f90:25-54, same rules; tau5 is implicitly typed REAL(4)."""
+    f = np.float32
+    eps = float(f(1e-16))
+    c13, c76, c116 = float(f(1.) / f(3.)), float(f(7.) / f(6.)), float(f(11.) / f(6.))
+    c16, c56 = float(f(1.) / f(6.)), float(f(5.) / f(6.))
+    qi1 = c13 * qmm - c76 * qm + c116 * q0
+    qi2 = -(c16 * qm) + c56 * q0 + c13 * qp
+    qi3 = c13 * q0 + c56 * qp - c16 * qpp
+    k1, k2 = float(f(13.) / f(12.)), .25
+    a1, a2 = qmm - 2 * qm + q0, qmm - 4 * qm + 3 * q0
+    b1, b2 = qm - 2 * q0 + qp, qm - qp
+    g1, g2 = q0 - 2 * qp + qpp, 3 * q0 - 4 * qp + qpp
+    beta1 = k1 * (a1 * a1) + k2 * (a2 * a2)
+    beta2 = k1 * (b1 * b1) + k2 * (b2 * b2)
+    beta3 = k1 * (g1 * g1) + k2 * (g2 * g2)
+    tau5 = float(f(abs(beta1 - beta3)))
+    w1 = 1. + tau5 / (beta1 + eps)
+    w2 = 6 * (1. + tau5 / (beta2 + eps))
+    w3 = 3 * (1. + tau5 / (beta3 + eps))
+    return (w1 * qi1 + w2 * qi2 + w3 * qi3) / (w1 + w2 + w3)
+
+
+def _flux1d_py(u, q):
+    """core/weno.f90:106-153 with 1-based indices kept."""
+    n = len(u)
+    U = lambda i: float(u[i - 1])          # noqa: E731
+    Q = lambda i: float(q[i - 1])          # noqa: E731
+    flux = np.zeros(n)
+    flux[0] = U(1) * Q(1) if U(1) > 0 else U(1) * _weno3_py(Q(3), Q(2), Q(1))
+    flux[1] = U(2) * _weno3_py(Q(1), Q(2), Q(3)) if U(2) > 0 else U(2) * _weno5_py(Q(5), Q(4), Q(3), Q(2), Q(1))
+    for i in range(3, n - 2):              # do i = 3, n-3
+        if U(i) > 0:
+            flux[i - 1] = U(i) * _weno5_py(Q(i - 2), Q(i - 1), Q(i), Q(i + 1), Q(i + 2))
+        else:
+            flux[i - 1] = U(i) * _weno5_py(Q(i + 3), Q(i + 2), Q(i + 1), Q(i), Q(i - 1))
+    i = n - 2
+    flux[i - 1] = U(i) * _weno5_py(Q(i - 2), Q(i - 1), Q(i), Q(i + 1), Q(i + 2)) if U(i) > 0 else \
+        U(i) * _weno3_py(Q(i + 2), Q(i + 1), Q(i))
+    i = n - 1
+    flux[i - 1] = U(i) * _weno3_py(Q(i - 1), Q(i), Q(i + 1)) if U(i) > 0 else U(i) * Q(i + 1)
+    flux[n - 1] = 0.
+    return flux
+
+
+def test_c_restatement_equals_an_independent_python_restatement():
+    """The C oracle (oracle/csrc/oracle_rhs.c) and a second transcription of weno.f90 made independently in
+    Python must agree bit for bit: smooth data, steps, tiny and huge magnitudes, still regions (beta = 0),
+    both wind signs, every line length down to the minimum of 5."""
+    rng = np.random.default_rng(77)
+    for scale in (1.0, 1e-8, 1e6, 1e-30):
+        for _ in range(300):
+            v = scale * rng.standard_normal(5)
+            assert K.weno5(*v) == _weno5_py(*[float(x) for x in v])
+            assert K.weno3(*v[:3]) == _weno3_py(*[float(x) for x in v[:3]])
+    for v in ([0.0] * 5, [1.0] * 5, [0, 0, 0, 1, 1], [1, 1, 0, 0, 0], [1e-200, 0, 0, 0, -1e-200], [2.5, 2.5, 2.5, 2.5, 3.5]):
+        v = [float(x) for x in v]
+        assert K.weno5(*v) == _weno5_py(*v)
+        assert K.weno3(*v[:3]) == _weno3_py(*v[:3])
+    for n in (5, 6, 7, 8, 13, 40):
+        for rep in range(5):
+            q = rng.standard_normal(n) * (10.0 ** rng.integers(-3, 3))
+            u = rng.standard_normal(n)
+            if rep == 0:
+                u[:] = np.abs(u)
+            if rep == 1:
+                u[:] = -np.abs(u)
+            if rep == 2:
+                u[::3] = 0.0
+            assert np.array_equal(K.flux1d(u, q), _flux1d_py(u, q)), "n = %d" % n
+
+
+def _loops(shape):
+    import itertools
+    return itertools.product(*[range(s) for s in shape])
+
+
+def test_c_kernels_equal_independent_python_loops():
+    """The remaining Fortran kernels of the right-hand side written a second time as plain Python loops over
+    the source (fortran_vortex_force.f90:10-165, fortran_upwind.f90:66-82, fortran_vorticity.f90:2-28,
+    fortran_kinenergy.f90:43-50, fortran_bernoulli.f90:2-97, fortran_dissipation.f90:2-35) against the C oracle,
+    bit for bit, on small ragged arrays."""
+    rng = np.random.default_rng(99)
+    for shape in [(5, 6, 7), (6, 5, 5), (3, 7, 9)]:
+        m_, n_, l_ = shape
+        U, vort, res0 = (rng.standard_normal(shape) for _ in range(3))
+        # vortex_force_direc: sweep along the last axis k, U averaged over (i, i+1), rows i < n-1
+        want = res0.copy()
+        for j in range(m_):
+            for i in range(n_ - 1):
+                UU_0, u1d = 0., np.zeros(l_)
+                for k in range(l_):
+                    UU_1 = 0.5 * (U[j, i, k] + U[j, i + 1, k])
+                    u1d[k] = 0.5 * (UU_0 + UU_1)
+                    UU_0 = UU_1
+                q = np.concatenate(([0.], vort[j, i, :l_ - 1]))
+                want[j, i, :] = want[j, i, :] - _flux1d_py(u1d, q)
+        got = res0.copy()
+        K.vortex_force_direc(U, vort, got)
+        assert np.array_equal(got, want)
+        # vortex_force_flip: sweep along the middle axis i, U averaged over (k, k+1), columns k < l-1, sign +
+        want = res0.copy()
+        for j in range(m_):
+            for k in range(l_ - 1):
+                UU_0, u1d = 0., np.zeros(n_)
+                for i in range(n_):
+                    UU_1 = 0.5 * (U[j, i, k] + U[j, i, k + 1])
+                    u1d[i] = 0.5 * (UU_0 + UU_1)
+                    UU_0 = UU_1
+                q = np.concatenate(([0.], vort[j, :n_ - 1, k]))
+                want[j, :, k] = want[j, :, k] + _flux1d_py(u1d, q)
+        got = res0.copy()
+        K.vortex_force_flip(U, vort, got)
+        assert np.array_equal(got, want)
+        # upwind: dtrac(1) -= flux(1); dtrac(i) += flux(i-1) - flux(i)
+        trac, u, d0 = (rng.standard_normal(shape) for _ in range(3))
+        want = d0.copy()
+        for k, j in _loops(shape[:2]):
+            flux = _flux1d_py(u[k, j], trac[k, j])
+            want[k, j, 0] = want[k, j, 0] - flux[0]
+            for i in range(1, shape[2]):
+                want[k, j, i] = want[k, j, i] + flux[i - 1] - flux[i]
+        got = d0.copy()
+        K.upwind(trac, u, got)
+        assert np.array_equal(got, want)
+        # vorticity: rows j < m-1, last column zero, last row untouched
+        ui, uj = rng.standard_normal(shape), rng.standard_normal(shape)
+        want = np.full(shape, 7.0)
+        for k in range(shape[0]):
+            for j in range(shape[1] - 1):
+                for i in range(shape[2] - 1):
+                    want[k, j, i] = uj[k, j, i + 1] - uj[k, j, i] - ui[k, j + 1, i] + ui[k, j, i]
+                want[k, j, -1] = 0.
+        got = np.full(shape, 7.0)
+        K.vorticity(ui, uj, got)
+        assert np.array_equal(got, want)
+        # kin: ke(i) += cff2*0.5*(u(i)^2 + u(i-1)^2), i >= 2
+        ke0, ds2 = rng.standard_normal(shape), 37.3
+        want, cff2 = ke0.copy(), 0.5 * ds2
+        for k, j in _loops(shape[:2]):
+            for i in range(1, shape[2]):
+                want[k, j, i] = want[k, j, i] + cff2 * 0.5 * (u[k, j, i] * u[k, j, i] + u[k, j, i - 1] * u[k, j, i - 1])
+        got = ke0.copy()
+        K.kin(u, u, got, ds2)
+        assert np.array_equal(got, want)
+        # gradke / gradkeandb / div / add_laplacian
+        ke, b, du0, dz = rng.standard_normal(shape), rng.standard_normal(shape), rng.standard_normal(shape), 0.31
+        want1, want2, cff = du0.copy(), du0.copy(), 0.5 * dz
+        wdiv0, wdiv1 = np.zeros(shape), du0.copy()
+        wlap, coef = du0.copy(), 0.013
+        for k, j in _loops(shape[:2]):
+            fxm = 0.
+            for i in range(shape[2] - 1):
+                want1[k, j, i] = want1[k, j, i] - (ke[k, j, i + 1] - ke[k, j, i])
+                want2[k, j, i] = want2[k, j, i] - (ke[k, j, i + 1] - ke[k, j, i]) + cff * (b[k, j, i + 1] + b[k, j, i])
+                fx = ke[k, j, i + 1] - ke[k, j, i]
+                wlap[k, j, i] = wlap[k, j, i] + coef * (fx - fxm)
+                fxm = fx
+            wlap[k, j, -1] = wlap[k, j, -1] + coef * (0. - fxm)
+            wdiv0[k, j, 0] = u[k, j, 0]
+            wdiv1[k, j, 0] = wdiv1[k, j, 0] + u[k, j, 0]
+            for i in range(1, shape[2]):
+                wdiv0[k, j, i] = u[k, j, i] - u[k, j, i - 1]
+                wdiv1[k, j, i] = wdiv1[k, j, i] + (u[k, j, i] - u[k, j, i - 1])
+        got = du0.copy(); K.gradke(ke, got); assert np.array_equal(got, want1)
+        got = du0.copy(); K.gradkeandb(ke, b, got, dz); assert np.array_equal(got, want2)
+        got = np.full(shape, 5.0); K.div(got, u, 0); assert np.array_equal(got, wdiv0)
+        got = du0.copy(); K.div(got, u, 1); assert np.array_equal(got, wdiv1)
+        got = du0.copy(); K.add_laplacian(ke, got, coef); assert np.array_equal(got, wlap)
+
+
+def _wrap(a, nh, xper, yper, zper):
+    """Periodic halo fill of a padded (nz, ny+2nh, nx+2nh) level array whose interior is at least nh wide in
+    every wrapped direction (mod_halo.f90:200-262 then reduces to: every halo cell of a wrapped direction is
+    a copy of the interior cell one period away; z planes are copied whole, after x and y)."""
+    nz, ny, nx = a.shape[0] - 2 * nh, a.shape[1] - 2 * nh, a.shape[2] - 2 * nh
+    if xper:
+        a[nh:-nh, nh:-nh, :nh] = a[nh:-nh, nh:-nh, nx:nx + nh]
+        a[nh:-nh, nh:-nh, -nh:] = a[nh:-nh, nh:-nh, nh:2 * nh]
+    if yper:
+        a[nh:-nh, :nh, nh:-nh] = a[nh:-nh, ny:ny + nh, nh:-nh]
+        a[nh:-nh, -nh:, nh:-nh] = a[nh:-nh, nh:2 * nh, nh:-nh]
+    if xper and yper:
+        for js, jd in ((slice(ny, ny + nh), slice(0, nh)), (slice(nh, 2 * nh), slice(-nh, None))):
+            for is_, id_ in ((slice(nx, nx + nh), slice(0, nh)), (slice(nh, 2 * nh), slice(-nh, None))):
+                a[nh:-nh, jd, id_] = a[nh:-nh, js, is_]
+    if zper:
+        a[:nh] = a[nz:nz + nh]
+        a[-nh:] = a[nh:2 * nh]
+
+
+@pytest.mark.parametrize("topology", [1, 6])
+def test_mg_operators_equal_independent_numpy_transcription(topology):
+    """mgfor's four level operators (basicoperators.f90:32-60, 173-231, 300-323, 363-400) written a second time
+    with NumPy slices in the source's summation order, against the C oracle, bit for bit -- closed box and
+    triply periodic box, random x / b including their halos."""
+    nh, n = 3, 8
+    mg = OracleMG(1, 1, n, n, n, nh, topology=topology)
+    per = topology == 6
+    rng = np.random.default_rng(12)
+    shape1 = mg.get_arrayshape(1)
+    x, b = rng.standard_normal(shape1), rng.standard_normal(shape1)
+    if per:
+        _wrap(x, nh, 1, 1, 1)
+        _wrap(b, nh, 1, 1, 1)
+    omega, cff1 = 0.9, 1.0 - 0.9
+    idiag, diag, msk = mg.get_array(ivar=6), mg.get_array(ivar=5), mg.get_array(ivar=7)
+
+    def S(a, ks, js, is_):
+        sh = lambda s, d: slice(s.start + d, s.stop + d)      # noqa: E731
+        return a[ks, js, sh(is_, -1)] + a[ks, js, sh(is_, 1)] + a[ks, sh(js, -1), is_] + a[ks, sh(js, 1), is_] + \
+            a[sh(ks, -1), js, is_] + a[sh(ks, 1), js, is_]
+
+    # ---- smooth: sweep 1 on the interior + 1 ring, sweep 2 on the interior, fill(x)
+    mg.set_array(x, ivar=1)
+    mg.set_array(b, ivar=2)
+    mg.set_array(np.zeros(shape1), ivar=4)
+    mg.op("smooth", 1)
+    y = np.zeros(shape1)
+    r1 = (slice(nh - 1, shape1[0] - nh + 1), slice(nh - 1, nh + n + 1), slice(nh - 1, nh + n + 1))
+    y[r1] = cff1 * x[r1] + omega * (S(x, *r1) - b[r1]) * idiag[r1]
+    it = (slice(nh, shape1[0] - nh), slice(nh, nh + n), slice(nh, nh + n))
+    xs = x.copy()
+    xs[it] = cff1 * y[it] + omega * (S(y, *it) - b[it]) * idiag[it]
+    if per:
+        _wrap(xs, nh, 1, 1, 1)
+    assert np.array_equal(mg.get_array(ivar=1), xs)
+    # ---- residual: r = msk*(b + diag*x - S(x)) on the interior, fill(r)
+    mg.op("residual", 1)
+    r = np.zeros(shape1)
+    r[it] = msk[it] * (b[it] + diag[it] * xs[it] - S(xs, *it))
+    if per:
+        _wrap(r, nh, 1, 1, 1)
+    got_r = mg.get_array(ivar=3)
+    assert np.array_equal(got_r[it], r[it])
+    if per:
+        assert np.array_equal(got_r, r)
+    # ---- restriction: b_c = Rcoef * sum of the 8 fine residuals in source order; x_c = 0; fill(b_c)
+    mg.op("restriction", 1)
+    shape2 = mg.get_arrayshape(2)
+    R = mg.get_array(ivar=8, lev=2)
+    nc = n // 2
+    bc = np.zeros(shape2)
+    for kc in range(nc):
+        for jc in range(nc):
+            for ic in range(nc):
+                k, j, i = nh + 2 * kc, nh + 2 * jc, nh + 2 * ic
+                s = r[k, j, i] + r[k, j, i + 1] + r[k, j + 1, i] + r[k, j + 1, i + 1] + \
+                    r[k + 1, j, i] + r[k + 1, j, i + 1] + r[k + 1, j + 1, i] + r[k + 1, j + 1, i + 1]
+                bc[nh + kc, nh + jc, nh + ic] = R[nh + kc, nh + jc, nh + ic] * s
+    if per:
+        _wrap(bc, nh, 1, 1, 1)
+    got_bc = mg.get_array(ivar=2, lev=2)
+    assert np.array_equal(got_bc[nh:-nh, nh:-nh, nh:-nh], bc[nh:-nh, nh:-nh, nh:-nh])
+    if per:
+        assert np.array_equal(got_bc, bc)
+    assert not mg.get_array(ivar=1, lev=2).any()
+    # ---- prolongation: x_f += Pcoef * (3 b + a | c) with the 9-3-3-1 weights of the nearest coarse cells; fill(x_f)
+    xc = rng.standard_normal(shape2)
+    if per:
+        _wrap(xc, nh, 1, 1, 1)
+    else:
+        xc[:nh] = 0; xc[-nh:] = 0; xc[:, :nh] = 0; xc[:, -nh:] = 0; xc[:, :, :nh] = 0; xc[:, :, -nh:] = 0
+    mg.set_array(xc, ivar=1, lev=2)
+    mg.op("prolongation", 1)
+    P = mg.get_array(ivar=9, lev=1)
+    xf = xs.copy()
+    for k in range(n):
+        for j in range(n):
+            for i in range(n):
+                kc, jc, ic = nh + k // 2, nh + j // 2, nh + i // 2
+                dk, dj, di = (1 if k % 2 else -1), (1 if j % 2 else -1), (1 if i % 2 else -1)
+
+                def plane(kk):
+                    return 9 * xc[kk, jc, ic] + 3 * xc[kk, jc, ic + di] + 3 * xc[kk, jc + dj, ic] + xc[kk, jc + dj, ic + di]
+                xf[nh + k, nh + j, nh + i] = xf[nh + k, nh + j, nh + i] + \
+                    P[nh + k, nh + j, nh + i] * (3 * plane(kc) + plane(kc + dk))
+    if per:
+        _wrap(xf, nh, 1, 1, 1)
+    assert np.array_equal(mg.get_array(ivar=1), xf)
