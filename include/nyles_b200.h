@@ -4,7 +4,7 @@
  * B200 (sm_100a) replacement for the two native layers under Nyles' LES time step:
  *   (1) the f2py Fortran kernels  core/fortran_{vorticity,vortex_force,upwind,kinenergy,
  *       bernoulli}.f90 + core/weno.f90          (reference interface: core/Makefile:1-2)
- *   (2) the ctypes-loaded multigrid library libmgmod64.so built from core/mgfor/*.f90
+ *   (2) the ctypes-loaded multigrid library libmgmod64.so built from core/mgfor/ (*.f90)
  *       (reference interface: core/mgfordriver.py:14-24, core/build.py:107-121,261-284)
  *
  * Conventions

@@ -146,3 +146,19 @@ def test_grid_matches_reference_formulas():
     assert np.allclose(g.x_vel["i"].view("i")[0, 0, :], x[0, 0, :] + 0.125)
     assert np.allclose(g.z_vor["i"].view("i")[:, 0, 0], (np.arange(10) + 0.5 - 3) * 0.25 + 0.125)
     assert g.y_b.view("j").shape == (14, 10, 10)
+
+
+def test_header_is_plain_c():
+    """The boundary is a C ABI: include/nyles_b200.h must compile as C99 and as C++ on its own (no torch, no CUDA
+    types in the signatures)."""
+    import subprocess
+    import tempfile
+    hdr = os.path.join(ROOT, "include", "nyles_b200.h")
+    for compiler, std, ext in (("gcc", "-std=c99", ".c"), ("g++", "-std=c++11", ".cpp")):
+        with tempfile.NamedTemporaryFile("w", suffix=ext, delete=False) as f:
+            f.write('#include "%s"\nint main(void) { return 0; }\n' % hdr)
+        env = dict(os.environ)
+        env.pop("CC", None)
+        out = subprocess.run([compiler, std, "-Wall", "-Werror", "-fsyntax-only", f.name], capture_output=True, text=True, env=env)
+        os.unlink(f.name)
+        assert out.returncode == 0, out.stderr
