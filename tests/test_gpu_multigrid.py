@@ -260,3 +260,27 @@ def test_obstacle_mask_rebuilds_the_operators(grid):
         np.testing.assert_allclose(g.stats["res"], o.reshist, rtol=1e-10, atol=0)
         assert np.array_equal(xg, xo)
         assert np.all(xg[3:-3, 3:-3, 3:-3][~fluid] == 0.0)        # nothing is ever written inside the obstacle
+
+
+def test_c_abi_example_runs(tmp_path):
+    """examples/c_abi_example.c -- plain C on the C ABI, no Python in the process -- solves the point-source problem
+    and reports the same V-cycle count and residual as the oracle."""
+    import re
+    import subprocess
+    from test_host_logic import build_c_example
+    exe = str(tmp_path / "c_abi_example")
+    r = build_c_example(exe)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    m = re.search(r"V-cycles (\d+), \|\|r\|\|\^2/\|\|b\|\|\^2 = (\S+),", out.stdout)
+    assert m, out.stdout
+    n = 64
+    o = OracleMG(1, 1, n, n, n, 3, 1)
+    b = np.zeros(o.shape)
+    b[3 + n // 4, 3 + n // 4, 3 + n // 4] = 1.0
+    b[3 + 3 * n // 4, 3 + 3 * n // 4, 3 + 3 * n // 4] = -1.0
+    x = np.zeros(o.shape)
+    o.solve(x, b)
+    assert int(m.group(1)) == o.nite
+    assert abs(float(m.group(2)) - o.res) <= 1e-3 * o.res        # printed with 4 significant digits

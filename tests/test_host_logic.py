@@ -162,3 +162,23 @@ def test_header_is_plain_c():
         out = subprocess.run([compiler, std, "-Wall", "-Werror", "-fsyntax-only", f.name], capture_output=True, text=True, env=env)
         os.unlink(f.name)
         assert out.returncode == 0, out.stderr
+
+
+def build_c_example(out):
+    import subprocess
+    env = dict(os.environ)
+    env.pop("CC", None)
+    libdir = os.path.join(ROOT, "nyles_b200")
+    cmd = ["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "examples", "c_abi_example.c"), "-L", libdir, "-lnyles_b200",
+           "-L/usr/local/cuda/lib64", "-lcudart", "-Wl,-rpath," + libdir, "-Wl,-rpath,/usr/local/cuda/lib64", "-o", out]
+    return subprocess.run(cmd, capture_output=True, text=True, env=env)
+
+
+def test_c_example_links_against_the_library(tmp_path):
+    """A host that is neither Python nor torch: examples/c_abi_example.c builds against include/nyles_b200.h and
+    links with libnyles_b200.so (it is RUN by the GPU suite)."""
+    from nyles_b200 import lib
+    lib.load()
+    r = build_c_example(str(tmp_path / "c_abi_example"))
+    assert r.returncode == 0, r.stderr
