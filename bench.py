@@ -438,7 +438,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="weak512")
-    ap.add_argument("--cpu-sample", default="rt128", help="bounded CPU sample of the workload")
+    # 256^3: 10-30 s of work for the 16 host threads of the GPU box, and (unlike 128^3) far out of the CPU's caches
+    ap.add_argument("--cpu-sample", default="rt256", help="bounded CPU sample of the workload")
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
