@@ -59,12 +59,26 @@ def workload(name, n_gpus):
                          % ("" if name == "weak512" else ", box extended along z"),
                     nx=nx, ny=ny, nz=nz, dx=0.25, geometry="closed", modelname="LES", ic="rt",
                     cfl=0.8, dt_max=0.1)
-    if name == "tgv256":           # configs[1]
-        return dict(name="taylor-green vortex 256^3, perio_xyz, Euler3d, LFAM3", nx=256, ny=256, nz=256 * n_gpus,
-                    dx=2 * np.pi / 256, geometry="perio_xyz", modelname="Euler3d", ic="tgv", cfl=0.8, dt_max=0.05)
+    if name.startswith("tgv"):     # tgv256 = configs[1]
+        n = int(name[3:])
+        return dict(name="taylor-green vortex %d^3, perio_xyz, Euler3d, LFAM3" % n, nx=n, ny=n, nz=n * n_gpus,
+                    dx=2 * np.pi / n, geometry="perio_xyz", modelname="Euler3d", ic="tgv", cfl=0.8, dt_max=0.4 * 32 / n)
     if name == "lock":             # configs[0]
         return dict(name="lock-exchange 128x32x32, closed, LES, LFAM3", nx=128, ny=32, nz=32 * n_gpus, dx=0.25,
                     geometry="closed", modelname="LES", ic="lock", cfl=0.8, dt_max=0.1)
+    if name == "rt512strong":      # configs[2] on 1 and 2 B200: ONE 512^3 box cut into z slabs (strong scaling)
+        return dict(name="rayleigh-taylor 512^3 (one box, %d z-slabs), closed, LES, LFAM3" % n_gpus, nx=512, ny=512,
+                    nz=512, dx=0.25, geometry="closed", modelname="LES", ic="rt", cfl=0.8, dt_max=0.1,
+                    scaling="strong")
+    if name in ("plume", "plume256"):
+        # configs[3]: experiments/forced_convection/forced_plume.py:14-80 scaled to 1024x1024x512 (L = 16x16x8),
+        # closed, LES, rotating f = 1, Gaussian-column heat source, linear stratification, cfl 0.8, dt_max 0.8;
+        # the box is fixed and cut into N z-slabs.  plume256: the same set-up at 256x256x128 (tests, one GPU)
+        f = 1 if name == "plume" else 4
+        return dict(name="turbulent plume %dx%dx%d (%d z-slabs), closed, LES, rotating + forced, LFAM3"
+                         % (1024 // f, 1024 // f, 512 // f, n_gpus), nx=1024 // f, ny=1024 // f, nz=512 // f,
+                    dx=16.0 / (1024 // f), geometry="closed", modelname="LES", ic="plume", cfl=0.8, dt_max=0.8,
+                    rotating=True, coriolis=1.0, forced=True, scaling="strong")
     if name.startswith("rt"):      # rtN: cubic RT box of N^3 per GPU (used for the CPU sample)
         n = int(name[2:])
         return dict(name="rayleigh-taylor %d^3, closed, LES, LFAM3" % n, nx=n, ny=n, nz=n * n_gpus, dx=0.25,
@@ -92,7 +106,33 @@ def initial_condition(w, x, y, z, rank):
         u = np.sin(X + 1.2) * np.cos(Y + 1.8) * np.cos(Z + 0.5) * dx
         v = -np.cos(X + 1.2) * np.sin(Y + 1.8) * np.cos(Z + 0.5) * dx
         return None, u, v
+    if w["ic"] == "plume":         # forced_plume.py:94-95: linear stratification b = 0.1 (z/Lz - 0.5), fluid at rest
+        return np.broadcast_to((0.1 * (z / Lz - 0.5))[:, None, None], shape).copy(), None, None
     raise ValueError(w["ic"])
+
+
+class PlumeForcing(object):
+    """The user forcing object of experiments/forced_convection/forced_plume.py:68-80: a heat source
+    Q = 0.1 exp(-z/0.02) (1 - tanh(d/0.1))/2 in a column around the axis of the box (x, y, z scaled by the box
+    lengths), added to db after the right-hand side.  `add` is the reference's protocol; `device_tendencies`
+    (nyles_b200) hands the same array to the fused RHS + time-scheme launches."""
+
+    def __init__(self, w, x, y, z, device=None):
+        X = x[None, None, :] / (w["nx"] * w["dx"]) - 0.5
+        Y = y[None, :, None] / (w["ny"] * w["dx"]) - 0.5
+        Z = z[:, None, None] / (w["nz"] * w["dx"])
+        msk = 0.5 * (1. - np.tanh(np.sqrt(X ** 2 + Y ** 2) / 0.1))
+        self.Q = 1e-1 * np.exp(-Z / 0.02) * msk
+        if device is not None:
+            import torch
+            self.Q = torch.as_tensor(self.Q, dtype=torch.float64).to(device)
+
+    def add(self, state, dstate, time):
+        db = dstate.b.view("i")
+        db += self.Q
+
+    def device_tendencies(self, state, time):
+        return {"b": self.Q}
 
 
 def bytes_per_cell_step(w, n_vc):
@@ -156,9 +196,11 @@ def cpu_reference_run(w, steps, warmup):
     os.environ["OMP_NUM_THREADS"] = str(threads)
     p = M.make_param(nx=w["nx"], ny=w["ny"], nz=w["nz"], geometry=w["geometry"], Lx=w["nx"] * w["dx"],
                      Ly=w["ny"] * w["dx"], Lz=w["nz"] * w["dx"], modelname=w["modelname"], cfl=w["cfl"],
-                     dt_max=w["dt_max"])
+                     dt_max=w["dt_max"], **{k: w[k] for k in ("rotating", "coriolis", "forced") if k in w})
     o = M.LES(p, flavour="fast")
     g = o.grid
+    if w.get("forced"):
+        o.forcing = PlumeForcing(w, g.x_b_1D, g.y_b_1D, g.z_b_1D)
     b, u, v = initial_condition(w, g.x_b_1D, g.y_b_1D, g.z_b_1D, 0)
     if b is not None:
         o.state.b.view("i")[:] = b
@@ -190,21 +232,35 @@ def cpu_model_string():
     return "unknown"
 
 
+def cpu_sample(args):
+    """The bounded sample of the workload that the CPU restatement is timed on (same IC, geometry and model on a
+    smaller box, rate quoted per cell), or -- `--cpu-sample same` -- the workload itself."""
+    name = args.cpu_sample
+    if name == "same":
+        return workload(args.workload, args.gpus), True
+    if name == "auto":
+        wl = args.workload
+        name = "plume256" if wl.startswith("plume") else "lock" if wl == "lock" else \
+            "tgv128" if wl.startswith("tgv") else "rt256"
+    return workload(name, 1), name == args.workload and args.gpus == 1
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = workload(args.cpu_sample, 1)
+    sample, is_workload = cpu_sample(args)
     w = workload(args.workload, args.gpus)
     value, ms, threads, n_vc = cpu_reference_run(sample, args.steps, args.warmup)
-    desc = ("%s: same IC/geometry/model as the workload on a %dx%dx%d sub-box, %d LFAM3 steps after 1 Euler + %d "
-            "warm-up steps; rate is per cell" % (sample["name"], sample["nx"], sample["ny"], sample["nz"],
-                                                 args.steps, args.warmup))
+    desc = ("%s: %s, %d LFAM3 steps after 1 Euler + %d warm-up steps; rate is per cell"
+            % (sample["name"], "the workload itself" if is_workload else
+               "same IC/geometry/model as the workload on a %dx%dx%d sub-box" % (sample["nx"], sample["ny"], sample["nz"]),
+               args.steps, args.warmup))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": w["name"], "sample": desc, "vcycles_per_step": n_vc,
-                       "cpu": cpu_model_string()},
+            "config": {"workload": w["name"], "sample": desc, "sample_is_the_workload": is_workload,
+                       "vcycles_per_step": n_vc, "cpu": cpu_model_string()},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -248,6 +304,17 @@ def traffic_from_ncu():
     return {}
 
 
+def comm_stats(steps):
+    """Slab exchanges and bytes pushed to the neighbours over NVLink by this rank, per step (ny_comm_stats)."""
+    from nyles_b200 import comm, lib
+    if not comm.active():
+        return None
+    import ctypes as C
+    n, b = C.c_longlong(), C.c_longlong()
+    lib.check(lib.load().ny_comm_stats(comm.get(), C.byref(n), C.byref(b), 1))
+    return {"exchanges_per_step": n.value / float(steps), "bytes_sent_per_step_per_rank": b.value / float(steps)}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -264,8 +331,20 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: no CUDA device is visible (there is no CPU fallback)")
     torch.cuda.set_device(local)
+    parity = None
     if world > 1:
+        # N-rank correctness travels with the scaling record: before anything is timed, three small problems
+        # (closed LES, perio_xyz Euler3d, perio_xy rotating LES; 64 x 64 x 64N) are stepped on ONE GPU by every
+        # rank and then on N z-slabs -- fields, dt and V-cycle counts must be bit-equal (nyles_b200/selfcheck.py)
+        from nyles_b200 import selfcheck
+        ref_runs = None if args.no_selfcheck else selfcheck.single_gpu_runs(world)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        if ref_runs is not None:
+            ok, report = selfcheck.slab_runs(ref_runs)
+            parity = ("ok" if ok else "FAILED", report)
+            del ref_runs
+            if not ok and rank == 0:
+                print("bench.py: slab self-check FAILED: %r" % (report,), file=sys.stderr)
 
     w = workload(args.workload, args.gpus)
     parameters.InextensibleDict.unfreeze()
@@ -277,9 +356,16 @@ def run_ours(args):
         w["nx"], w["ny"], w["nz"]
     up.MPI["npz"] = args.gpus
     up.time["cfl"], up.time["dt_max"] = w["cfl"], w["dt_max"]
+    for k in ("rotating", "coriolis", "forced"):
+        if k in w:
+            up.physics[k] = w[k]
     up.IO["datadir"] = ""                                   # no history output inside the benchmark
     ny = nyles.Nyles(up)
     model, g = ny.model, ny.grid
+    if w.get("forced"):                                     # "the user must attach the forcing to the model"
+        model.forcing = PlumeForcing(w, g.x_b_1D, g.y_b_1D, g.z_b_1D, device=model.state.b.tensor.device)
+        if args.unfused_forcing:                            # the reference's protocol only: RHS -> dstate -> add -> ts
+            model.forcing.device_tendencies = None
     b, u, v = initial_condition(w, g.x_b_1D, g.y_b_1D, g.z_b_1D, rank)
     if b is not None:
         model.state.b.view("i")[:] = b
@@ -309,6 +395,7 @@ def run_ours(args):
     euler = w["modelname"] == "Euler3d"
     barrier()
     lib.launch_count_reset()
+    comm_stats(1)                                          # reads and resets the exchange counters
     lib.prof_start()
     vc0 = model.mg.nvcycles
     sampler = ClockSampler(local)
@@ -332,6 +419,7 @@ def run_ours(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms = tt.item()
     value = cells * args.steps / (ms * 1e-3)
+    link = comm_stats(args.steps)
 
     # ---- timed region 2: through the host-buffer API (e2e) -----------------------------------
     host = ny.allocate_host_state()
@@ -403,7 +491,7 @@ def run_ours(args):
     # ---- CPU baseline beside it (rank 0, N = 1 only) -------------------------------------------
     cpu = None
     if world == 1 and not args.no_cpu:
-        sample = workload(args.cpu_sample, 1)
+        sample, _ = cpu_sample(args)
         v, cms, threads, cvc = cpu_reference_run(sample, args.cpu_steps, 1)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": "%s, %d LFAM3 steps timed after 1 Euler + 1 warm-up step (%.0f ms/step, %.1f V-cycles/step); "
@@ -411,7 +499,8 @@ def run_ours(args):
                          % (sample["name"], args.cpu_steps, cms, cvc, cpu_model_string())}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": w.get("scaling", "weak"),
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": w["name"], "grid": [w["nx"], w["ny"], w["nz"]], "cells": cells,
                        "parallelism": "z-slabs x%d" % world, "timestepping": "LFAM3",
@@ -421,6 +510,11 @@ def run_ours(args):
                        else "strict (source order, no FMA: bit-identical to the reference restatement)"},
             "roofline": roofline, "roofline_step": roofline_step, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": launches, "clocks": clocks}
+    if parity is not None:
+        line["parity_check"] = parity[0]
+        line["parity_check_detail"] = parity[1]
+    if link is not None:
+        line["nvlink"] = link
     emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -439,9 +533,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="weak512")
     # 256^3: 10-30 s of work for the 16 host threads of the GPU box, and (unlike 128^3) far out of the CPU's caches
-    ap.add_argument("--cpu-sample", default="rt256", help="bounded CPU sample of the workload")
+    ap.add_argument("--cpu-sample", default="auto",
+                    help="CPU sample: auto (a smaller box of the workload), a workload name, or `same`")
     ap.add_argument("--cpu-steps", type=int, default=3)
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--no-selfcheck", action="store_true", help="N > 1: skip the slabs-vs-one-GPU bit-equality check")
+    ap.add_argument("--unfused-forcing", action="store_true",
+                    help="plume: hide device_tendencies, i.e. run the reference's forcing.add protocol (unfused RHS)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--fast-arith", action="store_true", help="re-associated weno5 (see include/nyles_b200.h)")
     args = ap.parse_args()

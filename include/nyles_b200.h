@@ -168,11 +168,15 @@ int ny_rhs_update_u(ny_ctx*, const double* b, const double* Ux, const double* Uy
  *   mode 1 (Euler start-up) and 2 (LFAM3 predictor): out becomes the state, the old state array IS the
  *     "state copy" sn (and, for mode 1, is copied to sb);
  *   mode 3 (LFAM3 corrector, out = sn + dt ds): out becomes the state, sn becomes sb.
- * Mode 2 reads s and sb, mode 3 reads sn (s is still the array the stencils read), mode 1 reads s. */
+ * Mode 2 reads s and sb, mode 3 reads sn (s is still the array the stencils read), mode 1 reads s.
+ * add (NULL, or four pointers each of which may be NULL): user tendencies -- what a forcing object adds to
+ * dstate after the RHS (core/model_les.py:143-144, experiments/forced_convection/forced_plume.py:76-80) --
+ * added to the finished tendency of field f before its update, so a forced model keeps the fused path. */
 int ny_rhs_step(ny_ctx*, const double* Ux, const double* Uy, const double* Uz,
                 const double* wx, const double* wy, const double* wz, const double* ke,
                 const double* const s[4], const double* const sb[4], const double* const sn[4],
-                double* const out[4], int mode, double dt, double dz, int flags, ny_ext e, void* stream);
+                double* const out[4], const double* const add[4], int mode, double dt, double dz, int flags,
+                ny_ext e, void* stream);
 
 /* U_from_u + vorticity + kinenergy (core/model_les.py:112-123) in one pass over u */
 int ny_diag_post(ny_ctx*, const double* ux, const double* uy, const double* uz,
@@ -214,6 +218,9 @@ int  ny_comm_init(ny_ctx* ctx, int nranks, int rank, const char* id128, ny_comm*
 void ny_comm_free(ny_comm* comm);
 int  ny_comm_size(ny_comm* comm);
 int  ny_comm_rank(ny_comm* comm);
+/* face exchanges issued on this communicator and bytes this rank has sent to its slab neighbours (over NVLink
+ * peer memory, or through ncclSend on the fallback) since the last reset; a null comm reports zeros */
+int  ny_comm_stats(ny_comm* comm, long long* exchanges, long long* bytes_sent, int reset);
 /* sum (op_max = 0) or max (op_max != 0) of n <= 8 host doubles over all ranks; synchronises `stream`
  * (core/mpi/mpitools.py:28-32) */
 int  ny_comm_allreduce_host(ny_comm* comm, double* values_host, int n, int op_max, void* stream);
@@ -288,9 +295,11 @@ int  ny_mg_op(ny_mg*, int op, int lev, void* stream);
 /* ---- arithmetic primitives, exposed for the parity tests -------------------------------------
  * ny_debug_weno5: out[t] = weno5(q0[t], q1[t], q2[t], q3[t], q4[t]) (core/weno.f90:25-54) in the
  * context's arithmetic mode; q is 5 device arrays of n doubles stored back to back.
+ * ny_debug_weno3: out[t] = weno3(q0[t], q1[t], q2[t]) (core/weno.f90:1-22); q is 3 arrays back to back.
  * ny_debug_div: out[t] = the in-range division of ny_weno.cuh applied to a[t] / b[t]; mismatch_host
  * receives the number of t for which it differs (bitwise) from the IEEE quotient. */
 int  ny_debug_weno5(ny_ctx*, const double* q, double* out, long long n, void* stream);
+int  ny_debug_weno3(ny_ctx*, const double* q, double* out, long long n, void* stream);
 int  ny_debug_div(ny_ctx*, const double* a, const double* b, double* out, long long n,
                   long long* mismatch_host, void* stream);
 

@@ -101,6 +101,7 @@ extern "C" int ny_comm_init(ny_ctx* ctx, int nranks, int rank, const char* id128
     ny_comm* c = new ny_comm();
     c->ctx = ctx; c->nranks = nranks; c->rank = rank; c->nccl = nullptr; c->d_red = nullptr;
     memset(&c->p2p, 0, sizeof(c->p2p));
+    c->n_exchanges = 0; c->bytes_sent = 0;
     c->p2p.peer_rank[0] = c->p2p.peer_rank[1] = -1;
     { const char* e = getenv("NY_COMM_P2P"); if (e && e[0] == '0') c->p2p.state = -1; }
     ncclResult_t r = g_nccl.CommInitRank(&c->nccl, nranks, id, rank);
@@ -137,6 +138,15 @@ extern "C" void ny_comm_free(ny_comm* c)
     if (c->ev_ready) cudaEventDestroy(c->ev_ready);
     if (c->ev_done) cudaEventDestroy(c->ev_done);
     delete c;
+}
+
+extern "C" int ny_comm_stats(ny_comm* c, long long* exchanges, long long* bytes_sent, int reset)
+{
+    NY_REQUIRE(exchanges && bytes_sent, "null argument");
+    *exchanges = c ? c->n_exchanges : 0;
+    *bytes_sent = c ? c->bytes_sent : 0;
+    if (c && reset) { c->n_exchanges = 0; c->bytes_sent = 0; }
+    return NY_OK;
 }
 
 extern "C" int ny_comm_size(ny_comm* c) { return c ? c->nranks : 1; }
@@ -357,6 +367,7 @@ static int p2p_exchange(ny_comm* c, double* const* arrays, const size_t* plane, 
     if (below >= 0) { push.flag[0] = flag_of(p.peer[0], 1); pull.flag[0] = flag_of(p.local, 0); }
     if (above >= 0) { push.flag[1] = flag_of(p.peer[1], 0); pull.flag[1] = flag_of(p.local, 1); }
     const size_t moved = bytes * ((below >= 0) + (above >= 0));
+    c->n_exchanges++; c->bytes_sent += (long long)moved;
     const int sms = c->ctx->num_sms > 0 ? c->ctx->num_sms : 148;
     int nblk = (int)(moved >> 16);                  // one CTA per 64 KiB, 4 .. 2 per SM
     nblk = nblk < 4 ? 4 : (nblk > 2 * sms ? 2 * sms : nblk);
@@ -383,6 +394,7 @@ int ny_comm_exchange_z(ny_comm* c, double* const* arrays, int nf, size_t plane, 
         if (r != NY_OK || done) return r;
     }
     const size_t cnt = (size_t)nh * plane;
+    c->n_exchanges++; c->bytes_sent += (long long)(cnt * sizeof(double) * nf * ((below >= 0) + (above >= 0)));
     NY_NCCL(g_nccl.GroupStart());
     // sends first, then receives in the opposite neighbour order: when below == above (two ranks,
     // periodic z) NCCL matches per peer in posting order, and my low face is the peer's HIGH halo.
@@ -410,6 +422,8 @@ int ny_comm_exchange_z2(ny_comm* c, double* a0, size_t plane0, int nint0, double
         int r = p2p_exchange(c, arr, plane, los, nint, 2, nh, below, above, st, &done);
         if (r != NY_OK || done) return r;
     }
+    c->n_exchanges++;
+    c->bytes_sent += (long long)((size_t)nh * (plane0 + plane1) * sizeof(double) * ((below >= 0) + (above >= 0)));
     NY_NCCL(g_nccl.GroupStart());
     for (int f = 0; f < 2; f++) {                 // same posting order as ny_comm_exchange_z
         double* a = arr[f];

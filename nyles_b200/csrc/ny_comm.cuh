@@ -28,6 +28,7 @@ struct ny_comm {
     cudaStream_t xstream;     // high-priority stream for exchanges that overlap interior kernels
     cudaEvent_t ev_ready, ev_done;
     ny_p2p p2p;
+    long long n_exchanges, bytes_sent;   // face exchanges issued / bytes this rank pushed to its neighbours (ny_comm_stats)
 };
 
 // all return NY_OK or a negative ny_status; no-ops when c is null or has a single rank

@@ -40,7 +40,9 @@ __device__ __forceinline__ double lap_axis(double acc, const double* __restrict_
 // core/timescheme.py:131-175).  The kernel reads the tracer with a stencil, so the new value goes to a
 // separate array `out` and the caller rotates its buffers: mode 0: off (dtrac is stored), 1: Euler
 // start-up (out = s + dt ds), 2: LFAM3 predictor (reads sb), 3: LFAM3 corrector (out = sn + dt ds).
-struct TrUpd { int mode; double dt; const double* sb; const double* sn; double* out; };
+// add != nullptr: a user tendency (the array a forcing object adds to dtrac, core/model_les.py:143-144) is added to the
+// finished tendency before the update, as `forcing.add` does after the RHS.
+struct TrUpd { int mode; double dt; const double* sb; const double* sn; double* out; const double* add; };
 
 constexpr int UP_NW = 8;             // warps (rows) per CTA: UP_NW-1 output rows of 31 cells
 #ifndef UP_MINB
@@ -110,6 +112,7 @@ k_upwind2(const double* __restrict__ trac, const double* __restrict__ Ux, const 
                 if (DIFF) acc = lap_axis(acc, trac, c, e.sj, j, e.ny, cy);
                 acc = (k == 0) ? acc - Fz : acc + Fz_prev - Fz;
                 if (DIFF) acc = lap_axis(acc, trac, c, e.sk, k, e.nz, cz);
+                if (upd.add) acc = acc + upd.add[c];                  // model_les.py:143-144
                 if (upd.mode == 0) dtrac[c] = acc;
                 else if (upd.mode == 2) {                             // timescheme.py:144-162
                     const double v = zq[2], lf = told + (2. * upd.dt) * acc;
@@ -152,11 +155,12 @@ __device__ __forceinline__ double vf_flux(const double* __restrict__ US, const d
 // and b only, so updating u in place is race-free.
 // out[] != nullptr: rotating form -- only the new value is written, to out[] (the caller rotates its buffers:
 // the old u array becomes un, see ny_rhs_step); s, sb, sn are then read-only.
-struct TsUpd { int mode; double dt; double *s[3], *sb[3], *sn[3], *out[3]; };
+struct TsUpd { int mode; double dt; double *s[3], *sb[3], *sn[3], *out[3]; const double* add[3]; };
 
 __device__ __forceinline__ void ts_apply(const TsUpd& u, int comp, long long c, double ds)
 {
     double* __restrict__ s = u.s[comp];
+    if (u.add[comp]) ds = ds + u.add[comp][c];       // user tendency added after the RHS (model_les.py:143-144)
     if (u.out[comp]) {
         double* __restrict__ o = u.out[comp];
         if (u.mode == 2) {
@@ -272,6 +276,14 @@ k_debug_weno5(const double* __restrict__ q, double* __restrict__ out, long long 
 }
 
 __global__ void __launch_bounds__(256)
+k_debug_weno3(const double* __restrict__ q, double* __restrict__ out, long long n)
+{
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    out[t] = nyw::weno3(q[t], q[n + t], q[2 * n + t]);
+}
+
+__global__ void __launch_bounds__(256)
 k_debug_div(const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out, long long n,
             unsigned long long* __restrict__ mismatch)
 {
@@ -347,6 +359,14 @@ extern "C" int ny_debug_weno5(ny_ctx* ctx, const double* q, double* out, long lo
 {
     NY_REQUIRE(ctx && q && out && n > 0, "bad argument");
     k_debug_weno5<<<(unsigned)((n + 255) / 256), 256, 0, ny_stream(stream)>>>(q, out, n, ctx->fast_arith);
+    NY_CHECK_LAUNCH(ctx);
+    return NY_OK;
+}
+
+extern "C" int ny_debug_weno3(ny_ctx* ctx, const double* q, double* out, long long n, void* stream)
+{
+    NY_REQUIRE(ctx && q && out && n > 0, "bad argument");
+    k_debug_weno3<<<(unsigned)((n + 255) / 256), 256, 0, ny_stream(stream)>>>(q, out, n);
     NY_CHECK_LAUNCH(ctx);
     return NY_OK;
 }
@@ -459,7 +479,8 @@ extern "C" int ny_rhs_update_u(ny_ctx* ctx, const double* b, const double* Ux, c
 extern "C" int ny_rhs_step(ny_ctx* ctx, const double* Ux, const double* Uy, const double* Uz,
                            const double* wx, const double* wy, const double* wz, const double* ke,
                            const double* const s[4], const double* const sb[4], const double* const sn[4],
-                           double* const out[4], int mode, double dt, double dz, int flags, ny_ext e, void* stream)
+                           double* const out[4], const double* const add[4], int mode, double dt, double dz, int flags,
+                           ny_ext e, void* stream)
 {
     NY_REQUIRE(s && sb && sn && out && mode >= 1 && mode <= 3, "bad argument");
     const bool euler = flags & 1;
@@ -474,10 +495,11 @@ extern "C" int ny_rhs_step(ny_ctx* ctx, const double* Ux, const double* Uy, cons
     for (int a = 0; a < 3; a++) {
         upd.s[a] = const_cast<double*>(s[a + 1]); upd.sb[a] = const_cast<double*>(sb[a + 1]);
         upd.sn[a] = const_cast<double*>(sn[a + 1]); upd.out[a] = out[a + 1];
+        upd.add[a] = add ? add[a + 1] : nullptr;
     }
     TrUpd tupd;
     memset(&tupd, 0, sizeof(tupd));
-    if (!euler) { tupd.mode = mode; tupd.dt = dt; tupd.sb = sb[0]; tupd.sn = sn[0]; tupd.out = out[0]; }
+    if (!euler) { tupd.mode = mode; tupd.dt = dt; tupd.sb = sb[0]; tupd.sn = sn[0]; tupd.out = out[0]; tupd.add = add ? add[0] : nullptr; }
     return rhs_impl(ctx, euler ? nullptr : s[0], Ux, Uy, Uz, wx, wy, wz, ke, nullptr, nullptr, nullptr, nullptr, dz, flags,
                     e, stream, &upd, euler ? nullptr : &tupd);
 }

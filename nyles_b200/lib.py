@@ -60,7 +60,7 @@ _PROTOS = {
     "ny_add_laplacian": ([_P, _P, _P, _D, _D, _D, ny_ext, _P], _I),
     "ny_rhs": ([_P] + [_P] * 12 + [_D, _I, ny_ext, _P], _I),
     "ny_rhs_update_u": ([_P] + [_P] * 9 + [C.POINTER(_P * 3)] * 3 + [_I, _D, _D, _I, ny_ext, _P], _I),
-    "ny_rhs_step": ([_P] + [_P] * 7 + [C.POINTER(_P * 4)] * 4 + [_I, _D, _D, _I, ny_ext, _P], _I),
+    "ny_rhs_step": ([_P] + [_P] * 7 + [C.POINTER(_P * 4)] * 4 + [_P] + [_I, _D, _D, _I, ny_ext, _P], _I),
     "ny_ts_axpy": ([_P, _P, _P, _D, _LL, _P], _I),
     "ny_ts_lfam3_first": ([_P, _P, _P, _P, _P, _D, _LL, _P], _I),
     "ny_ts_lfam3_pred": ([_P, _P, _P, _P, _P, _D, _LL, _P], _I),
@@ -72,6 +72,7 @@ _PROTOS = {
     "ny_comm_unique_id": ([C.c_char_p], _I),
     "ny_comm_init": ([_P, _I, _I, C.c_char_p, C.POINTER(_P)], _I),
     "ny_comm_free": ([_P], None),
+    "ny_comm_stats": ([_P, C.POINTER(_LL), C.POINTER(_LL), _I], _I),
     "ny_comm_size": ([_P], _I),
     "ny_comm_rank": ([_P], _I),
     "ny_comm_allreduce_host": ([_P, C.POINTER(_D), _I, _I, _P], _I),
@@ -100,6 +101,7 @@ _PROTOS = {
     "ny_mg_op": ([_P, _I, _I, _P], _I),
     "ny_diag_post_max_speed2": ([_P, C.POINTER(_D), _P], _I),
     "ny_debug_weno5": ([_P, _P, _P, _LL, _P], _I),
+    "ny_debug_weno3": ([_P, _P, _P, _LL, _P], _I),
     "ny_debug_div": ([_P, _P, _P, _P, _LL, C.POINTER(_LL), _P], _I),
 }
 

@@ -46,7 +46,7 @@ class LES(object):
         self.halo = halo.set_halo(param, self.state)
         self.neighbours = param["neighbours"]
         self.timescheme = ts.Timescheme(param, self.state)
-        self.timescheme.set(self.rhs, self.diagnose_var, self.rhs_update_u, self.rhs_step, self._rest_rhs)
+        self.timescheme.set(self.rhs, self.diagnose_var, self.rhs_step, self._rest_rhs)
         self.orderA, self.orderVF, self.orderKE = param["orderA"], param["orderVF"], param["orderKE"]
         self.rotating = param["rotating"]
         self.forced = param["forced"]
@@ -77,7 +77,7 @@ class LES(object):
             return None
         state, epoch, versions, ptrs = key
         U = state.U
-        if state is not self.state or epoch != lib.u_epoch or versions != tuple(U[d].tensor._version for d in "ijk") or \
+        if state is not self.state or epoch != lib.u_epoch or versions is None or versions != _versions(U) or \
                 ptrs != tuple(U[d].tensor.data_ptr() for d in "ijk"):
             return None
         out = lib.C.c_double()
@@ -110,7 +110,7 @@ class LES(object):
                     self.grid.idx2, self.grid.idy2, self.grid.idz2, float(self.fparameter), lib.ext(t), lib.stream()))
                 # the launch also left max(U^2+V^2+W^2) on the device; valid until U is written again
                 lib.u_epoch += 1
-                self._umax_key = (state, lib.u_epoch, tuple(U[d].tensor._version for d in "ijk"),
+                self._umax_key = (state, lib.u_epoch, _versions(U),
                                   tuple(U[d].tensor.data_ptr() for d in "ijk"))
                 self.halo.fill(state.vor, local_only=lazy)
                 self.halo.fill(state.ke, local_only=lazy)
@@ -165,41 +165,28 @@ class LES(object):
         if self.euler:
             dstate.b.tensor.zero_()
 
-    def rhs_update_u(self, state, t, dstate, mode, dt, stateb, staten, last=False):
-        """rhs() followed by the time-scheme update of u (mode 1: LFAM3 start-up, 2: predictor, 3: corrector)
-        in one momentum launch; dstate.b is filled as by rhs(), dstate.u is not.  Returns False -- and does
-        nothing -- when something has to see the velocity tendency first (viscosity, forcing)."""
-        if not self.fused or (last and self.add_viscosity) or self.forced:
-            return False
-        U, w = state.U, state.vor
-        t0 = U["i"].tensor
-        flags = (1 if self.euler else 0) | (0 if self.nonlinear else 2)
-
-        def ptr3(vec):
-            return lib.C.byref((lib.C.c_void_p * 3)(*[lib.ptr(vec[d].tensor).value for d in "ijk"]))
-        lib.check(lib.load().ny_rhs_update_u(
-            lib.context(t0.device), lib.ptr(None if self.euler else state.b.tensor),
-            lib.ptr(U["i"].tensor), lib.ptr(U["j"].tensor), lib.ptr(U["k"].tensor),
-            lib.ptr(w["i"].tensor), lib.ptr(w["j"].tensor), lib.ptr(w["k"].tensor), lib.ptr(state.ke.tensor),
-            lib.ptr(None if self.euler else dstate.b.tensor), ptr3(state.u), ptr3(stateb.u), ptr3(staten.u),
-            mode, dt, self.grid.dz, flags, lib.ext(t0), lib.stream()))
-        if self.euler:
-            dstate.b.tensor.zero_()
-        if len(self.traclist) > 1:
-            saved, self.tracer.traclist = self.tracer.traclist, self.traclist[1:]
-            self.tracer.rhstrac(state, dstate)
-            self.tracer.traclist = saved
-        return True
-
     def rhs_step(self, state, t, mode, dt, stateb, staten, last=False):
         """rhs() and the time-scheme update of b and u in the two RHS launches themselves (ny_rhs_step;
         mode 1: LFAM3 start-up, 2: predictor, 3: corrector): no tendency is stored and each field is written
         once, into the buffer that the scheme no longer needs; the buffers of state / stateb / staten are
         then rotated (core/timescheme.py:131-175 leaves the same values in the same-named arrays).
         Returns the names it has updated, or None -- having done nothing -- when something must see the
-        tendencies first (viscosity, forcing) or the fused path is off."""
-        if not self.fused or (last and self.add_viscosity) or self.forced:
+        tendencies first or the fused path is off:
+          * viscosity: the corrector adds the Laplacian of u to du (model_les.py:141-142).  The decision is
+            taken per MODEL, not per call: the rotating predictor defers `stateb := state n` to the rotation
+            of the corrector, so a step must not mix a fused predictor with an unfused corrector;
+          * a forcing object that only offers the reference's `add(state, dstate, t)`.  A forcing object that
+            also offers `device_tendencies(state, t) -> {nickname: tensor}` (what it would add to dstate,
+            canonical (k,j,i) CUDA tensors, e.g. {"b": Q}) keeps the fused path: the kernels add those arrays
+            to the finished tendencies exactly where `forcing.add` would."""
+        if not self.fused or self.add_viscosity:
             return None
+        add = {}
+        if self.forced:
+            fn = getattr(self.forcing, "device_tendencies", None)
+            if fn is None:
+                return None
+            add = fn(state, t) or {}
         U, w = state.U, state.vor
         t0 = U["i"].tensor
         flags = (1 if self.euler else 0) | (0 if self.nonlinear else 2)
@@ -209,10 +196,21 @@ class LES(object):
         def ptr4(st):
             p = [lib.ptr(None if self.euler else st.b.tensor).value] + [lib.ptr(st.u[d].tensor).value for d in "ijk"]
             return lib.C.byref((lib.C.c_void_p * 4)(*p))
+        addp = None
+        if add:
+            unknown = set(add) - set(names)
+            if unknown:
+                raise ValueError("device_tendencies: %s is not a prognostic field of the fused step" % sorted(unknown))
+            tens = [add.get(n) for n in (["b"] if not self.euler else [None]) + ["u_i", "u_j", "u_k"]]
+            tens = [getattr(a, "tensor", a) for a in tens]
+            for a in tens:
+                if a is not None and tuple(a.shape) != tuple(t0.shape):
+                    raise ValueError("device_tendencies: arrays must have the shape of the fields, %s" % (tuple(t0.shape),))
+            addp = lib.C.byref((lib.C.c_void_p * 4)(*[lib.ptr(a).value for a in tens]))
         lib.check(lib.load().ny_rhs_step(
             lib.context(t0.device), lib.ptr(U["i"].tensor), lib.ptr(U["j"].tensor), lib.ptr(U["k"].tensor),
             lib.ptr(w["i"].tensor), lib.ptr(w["j"].tensor), lib.ptr(w["k"].tensor), lib.ptr(state.ke.tensor),
-            ptr4(state), ptr4(stateb), ptr4(staten), ptr4(outs), mode, dt, self.grid.dz, flags, lib.ext(t0),
+            ptr4(state), ptr4(stateb), ptr4(staten), ptr4(outs), addp, mode, dt, self.grid.dz, flags, lib.ext(t0),
             lib.stream()))
         for name in names:
             S, B, N = state.get(name), stateb.get(name), staten.get(name)
@@ -247,6 +245,14 @@ class LES(object):
     def write_stats(self, path):
         with open("%s/stats.pkl" % path, "bw") as fid:
             pickle.dump(self.stats, fid)
+
+
+def _versions(U):
+    """Write counters of the three U tensors (torch bumps `_version` on every in-place write; it is the
+    counter autograd's own saved-tensor check reads).  A torch build without it gives None, which never
+    matches: the cached maximum is then simply not used."""
+    v = tuple(getattr(U[d].tensor, "_version", None) for d in "ijk")
+    return None if None in v else v
 
 
 def reset_state(state):

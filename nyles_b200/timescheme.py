@@ -35,30 +35,23 @@ class Timescheme(object):
             self.before_last_diagnose(state)
         self.diagnose_var(state)
 
-    def set(self, rhs, diagnose_var, rhs_update_u=None, rhs_step=None, tracer_rhs=None):
+    def set(self, rhs, diagnose_var, rhs_step=None, tracer_rhs=None):
         self.rhs = rhs
         self.diagnose_var = diagnose_var
-        # optional: rhs + update of the velocity components in one launch (model_les.LES.rhs_update_u)
-        self.rhs_update_u = rhs_update_u
         # optional: rhs + update of b and u inside the RHS launches, with buffer rotation (LES.rhs_step);
         # tracer_rhs(state, dstate) then supplies the tendencies of the remaining (passive) tracers
         self.rhs_step = rhs_step
         self.tracer_rhs = tracer_rhs
 
     def _rhs_and_update(self, state, t, mode, dt, last, others, fn):
-        """The right-hand side and the update `fn` of every prognostic scalar; the velocity components are
-        updated by the model's fused launch when it offers one."""
+        """The right-hand side and the update `fn` of every prognostic scalar; b and the velocity components
+        are updated by the model's fused launches when it offers them (rhs_step), else by `fn`."""
         skip = None
         if self.rhs_step is not None:
             skip = self.rhs_step(state, t, mode, dt, self.stateb, self.state, last=last)
             if skip is not None and len(skip) < len(self.prognostic_scalars):
                 self.tracer_rhs(state, self.dstate)
-        if skip is not None:
-            pass
-        elif self.rhs_update_u is not None and \
-                self.rhs_update_u(state, t, self.dstate, mode, dt, self.stateb, self.state, last=last):
-            skip = ("u_i", "u_j", "u_k")
-        else:
+        if skip is None:
             self.rhs(state, t, self.dstate, last=last)
         for name in self.prognostic_scalars:
             if skip and name in skip:

@@ -47,16 +47,20 @@ class FieldView(object):
 
     __array_priority__ = 100
 
-    def __init__(self, tensor=None, owner=None, axes=None):
+    def __init__(self, tensor=None, owner=None, axes=None, index=()):
         # A view taken from a Scalar is bound to the Scalar, not to its current buffer: the fused time
         # step rotates the buffers of the prognostic fields (model_les.LES.rhs_step), and a view kept
-        # across steps -- as NumPy views of the reference may be -- must keep showing the field.
-        self._tensor, self._owner, self._axes = tensor, owner, axes
+        # across steps -- as NumPy views of the reference may be -- must keep showing the field.  The same
+        # holds for sub-views (b.view("i")[k0:k1]): they keep the chain of indices and re-apply it.
+        self._tensor, self._owner, self._axes, self._index = tensor, owner, axes, tuple(index)
 
     @property
     def tensor(self):
         if self._owner is not None:
-            return self._owner.tensor.permute(*self._axes)
+            t = self._owner.tensor.permute(*self._axes)
+            for idx in self._index:
+                t = t[idx]
+            return t
         return self._tensor
 
     # --- conversions
@@ -88,7 +92,11 @@ class FieldView(object):
     # --- indexing
     def __getitem__(self, idx):
         out = self.tensor[idx]
-        return FieldView(out) if out.ndim > 0 else out.item()
+        if out.ndim == 0:
+            return out.item()
+        if self._owner is not None:
+            return FieldView(owner=self._owner, axes=self._axes, index=self._index + (idx,))
+        return FieldView(out)
 
     def __setitem__(self, idx, value):
         self.tensor[idx] = self._coerce(value)

@@ -158,6 +158,10 @@ CASES = {
     # rotating frame + a user forcing object, as experiments/forced_convection/forced_plume.py sets them up
     "les_closed_forced_rot": ("LES", "closed", (8, 8, 16), (1.0, 1.0, 2.0),
                               {"forced": True, "rotating": True, "coriolis": 1.0, "forcing": "plume", "uamp": 0.5}, 3),
+    # LFAM3 with viscosity and tracer diffusion (diff_coef): the corrector adds the Laplacians (model_les.py:141-142,
+    # tracer.py:74-77), the leapfrog predictor does not -- the buffers of both must stay consistent across steps
+    "les_closed_lfam3_visc": ("LES", "closed", (8, 8, 16), (1.0, 1.0, 2.0),
+                              {"diff_coef": {"u": 5e-3, "b": 2e-3}, "uamp": 1.0}, 6),
 }
 
 

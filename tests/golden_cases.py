@@ -18,6 +18,7 @@ CASES = {
     # the plume set-up of experiments/forced_convection/forced_plume.py: rotating frame + user forcing object
     "les_closed_forced_rot": ("LES", "closed", (8, 8, 16), (1.0, 1.0, 2.0),
                               {"forced": True, "rotating": True, "coriolis": 1.0, "forcing": "plume"}, 3),
+    "les_closed_lfam3_visc": ("LES", "closed", (8, 8, 16), (1.0, 1.0, 2.0), {"diff_coef": {"u": 5e-3, "b": 2e-3}}, 6),
 }
 
 SCALARS = ("b", "p", "ke", "div")
@@ -56,6 +57,19 @@ class PlumeForcing(object):
         db += self.Q
 
 
-def forcing_of(name, param, grid):
+class DevicePlumeForcing(PlumeForcing):
+    """The same forcing, additionally offering nyles_b200's `device_tendencies` protocol (the arrays `add` would
+    add to dstate, resident on the GPU), which keeps the model on its fused RHS + time-scheme launches."""
+
+    def device_tendencies(self, state, time):
+        import torch
+        if getattr(self, "_Qd", None) is None:
+            self._Qd = torch.as_tensor(np.ascontiguousarray(self.Q), dtype=torch.float64).to(state.b.tensor.device)
+        return {"b": self._Qd}
+
+
+def forcing_of(name, param, grid, device=False):
     kind = CASES[name][4].get("forcing")
-    return PlumeForcing(param, grid) if kind == "plume" else None
+    if kind != "plume":
+        return None
+    return DevicePlumeForcing(param, grid) if device else PlumeForcing(param, grid)

@@ -224,11 +224,15 @@ def test_fused_rhs_equals_operator_sequence(K, L, shape, flags):
 @pytest.mark.parametrize("shape", SHAPES[1:] + [(40, 37, 70)])
 @pytest.mark.parametrize("mode", [1, 2, 3])
 @pytest.mark.parametrize("flags", [0, 1, 2])
-def test_rhs_step_equals_rhs_then_timescheme(L, shape, mode, flags):
+@pytest.mark.parametrize("forced", [False, True])
+def test_rhs_step_equals_rhs_then_timescheme(L, shape, mode, flags, forced):
     """ny_rhs_step (the RHS kernels apply the LFAM3 / Euler update and write each field once, into a
     separate buffer) against ny_rhs followed by the ny_ts_* kernels: bit-identical new state, and none
-    of the arrays it only reads is touched."""
+    of the arrays it only reads is touched.  forced: user tendencies (what a forcing object adds to dstate after
+    the RHS, core/model_les.py:143-144) for b and two of the velocity components."""
     euler = flags & 1
+    if forced and shape != SHAPES[1]:
+        pytest.skip("user tendencies are exercised on one shape")
     b, ke, sb_b, sn_b = rand_fields(shape, 4, 40)
     U, w, u, ub, un = (rand_fields(shape, 3, 41 + n) for n in range(5))
     dz, dt = 0.25, 0.0137
@@ -243,6 +247,15 @@ def test_rhs_step_equals_rhs_then_timescheme(L, shape, mode, flags):
     L.check(lib.ny_rhs(L.context(), L.ptr(s[0]), *[L.ptr(t) for t in gU + gw], L.ptr(gke), L.ptr(ds[0]),
                        *[L.ptr(t) for t in ds[1:]], dz, flags, L.ext(s[0]), L.stream()))
     fields = range(1, 4) if euler else range(4)
+    addp = None
+    if forced:
+        Q = [g(a) for a in rand_fields(shape, 4, 77)]
+        Q[2] = None                                          # a field without user tendency
+        for f in fields:
+            if Q[f] is not None:
+                ds[f] += Q[f]                                # forcing.add(state, dstate, t)
+        addp = C.byref((C.c_void_p * 4)(*[None if (q is None or (euler and n == 0)) else L.ptr(q).value
+                                          for n, q in enumerate(Q)]))
     for f in fields:
         n = s[f].numel()
         if mode == 1:
@@ -260,7 +273,7 @@ def test_rhs_step_equals_rhs_then_timescheme(L, shape, mode, flags):
     def ptr4(ts):
         return C.byref((C.c_void_p * 4)(*[None if (euler and n == 0) else L.ptr(t).value for n, t in enumerate(ts)]))
     L.check(lib.ny_rhs_step(L.context(), *[L.ptr(t) for t in gU + gw], L.ptr(gke), ptr4(s2), ptr4(sb2), ptr4(sn2),
-                            ptr4(out), mode, dt, dz, flags, L.ext(s2[0]), L.stream()))
+                            ptr4(out), addp, mode, dt, dz, flags, L.ext(s2[0]), L.stream()))
     for f in fields:
         assert np.array_equal(host(out[f]), host(s[f])), "field %d" % f
         # read-only inputs stay as they were
@@ -273,7 +286,7 @@ def test_rhs_step_equals_rhs_then_timescheme(L, shape, mode, flags):
             assert np.array_equal(host(sn[f]), host(s2[f])) and np.array_equal(host(sb[f]), host(s2[f]))
     # aliasing the output with an array the launch reads is refused
     assert lib.ny_rhs_step(L.context(), *[L.ptr(t) for t in gU + gw], L.ptr(gke), ptr4(s2), ptr4(sb2), ptr4(sn2),
-                           ptr4(s2 if mode != 3 else sn2), mode, dt, dz, flags, L.ext(s2[0]), L.stream()) != 0
+                           ptr4(s2 if mode != 3 else sn2), None, mode, dt, dz, flags, L.ext(s2[0]), L.stream()) != 0
 
 
 @pytest.mark.parametrize("shape", SHAPES[:3])
@@ -465,3 +478,28 @@ def test_weno5_primitive_against_oracle(fast):
     else:
         scale = np.max(np.abs(q), axis=0) + 1e-300
         assert np.max(np.abs(got - ref) / scale) <= 1e-13
+
+
+def test_weno3_primitive_against_oracle():
+    """weno3 (core/weno.f90:1-22; the closure of flux1d next to the line ends) on smooth, sharp, still, constant,
+    round-off-noise and tiny stencils, bitwise against the oracle (there is one arithmetic mode: the edge faces
+    always run the source-order code)."""
+    from nyles_b200 import lib
+    o = Kernels("strict")
+    rng = np.random.default_rng(78)
+    n = 20000
+    q = rng.standard_normal((3, n))
+    q[:, :2000] = 0.0
+    q[:, 2000:4000] = 1.0
+    q[:, 4000:6000] *= 1e-12
+    q[:, 6000:8000] = 1.0 + 1e-16 * rng.integers(-3, 4, (3, 2000))
+    q[:, 8000:10000] = np.sign(q[:, 8000:10000])
+    q[:, 10000:12000] *= 1e-23
+    q[:, 12000:14000] *= 1e-150
+    q[:, 14000:16000] *= 1e+100
+    ref = np.array([o.weno3(*q[:, t]) for t in range(n)])
+    L = lib.load()
+    qd = torch.as_tensor(q, device="cuda").contiguous()
+    out = torch.empty(n, dtype=torch.float64, device="cuda")
+    lib.check(L.ny_debug_weno3(lib.context(), lib.ptr(qd), lib.ptr(out), n, lib.stream()))
+    assert np.array_equal(out.cpu().numpy(), ref)
