@@ -98,6 +98,11 @@ const char* ny_prof_name(int tag);
  * Differences are a few ulp, far inside the 1e-12 parity bar (tests/test_gpu_operators.py). */
 int  ny_set_arith(ny_ctx* ctx, int fast);
 int  ny_get_arith(ny_ctx* ctx);
+/* Which kernel evaluates the fused momentum right-hand side on the cells whose six WENO sweeps are interior
+ * (3 <= s <= n-4 on every axis): 0 (default) = the plane-marching TMA kernel for grids of at least 2^18 cells,
+ * the cell-parallel kernel below that; 1 = always the cell-parallel kernel; 2 = the TMA kernel wherever it is
+ * legal (even nx, 16-byte aligned arrays).  Both are bit-identical; the switch exists for tests and timing. */
+int  ny_set_momentum_variant(ny_ctx* ctx, int variant);
 
 /* ---- f2py kernel replacements ------------------------------------------------------ */
 /* fortran_vorticity.vorticity x3 as driven by core/vorticity.py:7-34 (fparam = f*dx*dy, 0 = off) */

@@ -1,5 +1,6 @@
 // Context management and error reporting of libnyles_b200.so.
 #include "ny_common.cuh"
+#include <cstdlib>
 
 static thread_local char g_err[512] = "";
 
@@ -36,6 +37,8 @@ extern "C" int ny_init(int device, ny_ctx** out)
     ctx->num_sms = prop.multiProcessorCount;
     ctx->launches = 0;
     ctx->fast_arith = 0;
+    ctx->mom_variant = 0;
+    { const char* v = getenv("NY_MOM_VARIANT"); if (v && *v >= '0' && *v <= '2') ctx->mom_variant = *v - '0'; }
     ctx->scratch_doubles = 1 << 16;
     ctx->d_scratch = nullptr;
     ctx->h_pinned = nullptr;

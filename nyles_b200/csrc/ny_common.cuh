@@ -16,6 +16,7 @@ struct ny_ctx {
     int num_sms;
     long long launches;
     int fast_arith;           // WENO arithmetic mode, see ny_weno.cuh (0 = strict / bit-exact)
+    int mom_variant;          // momentum kernel choice, see ny_set_momentum_variant (0 = by size)
     double* d_scratch;        // reduction partials (device)
     size_t scratch_doubles;
     double* h_pinned;         // small pinned mailbox for scalars

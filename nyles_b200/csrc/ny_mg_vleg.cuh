@@ -65,9 +65,14 @@ struct VlegCtx {
     double omega, cff1;
     int cA0, cA1, cB0, cB1;            // in-plane neighbour counts (negative: cell outside the domain)
     double rA0, rA1, rB0, rB1;         // 1 / (count + 2)
-    bool oc0, oc1, orA, orB;           // cell belongs to the stored tile and to the interior
+    // which cells of the patch belong to the stored tile and to the interior, as ONE register of flags (made opaque
+    // to the compiler, which otherwise re-derives every flag from threadIdx in every plane to save registers):
+    // bits 0-2: row A stores both / only .x / only .y; bits 3-5: the same for row B; bits 6-9: cell A.x, A.y, B.x,
+    // B.y counts in the residual norm; bit 7 also guards the restriction store
+    unsigned sf;
     int oA, oUp, oDn, oC;              // shared-memory offsets (doubles) inside a plane / coarse tile
-    long long gA;                      // global offset of (row A, column .x) inside a plane
+    unsigned gA, sk32;                 // element offset of (row A, column .x) inside a plane; plane stride (a level has < 2^32 cells)
+    unsigned bcA, csk32;               // coarse cell under the patch (row, column part of its offset); coarse plane stride
     int exA0, exA1, exB0, exB1;
     int ai, ajA;
     int k0, k1, pb1, pb2, pb3;
@@ -171,18 +176,17 @@ __device__ __forceinline__ void vleg_plane(const VlegCtx& c, int p, int t, const
             st2(pz + oB, zp.B);
         }
         if (FAST || (q >= c.k0 && q < c.k1)) {
-            double* const dA = c.xo + (long long)q * g.sk + c.gA;
+            // independent single-instruction bodies: predicated stores, no branches (lanes 1 and 30 of every warp
+            // hold a column pair that straddles the edge of the stored tile)
+            double* const dA = c.xo + ((unsigned)q * c.sk32 + c.gA);
             double* const dB = dA + g.sj;
-            if (c.orA) {
-                if (c.oc0 && c.oc1) st2(dA, zp.A);
-                else if (c.oc0) dA[0] = zp.A.x;
-                else if (c.oc1) dA[1] = zp.A.y;
-            }
-            if (c.orB) {
-                if (c.oc0 && c.oc1) st2(dB, zp.B);
-                else if (c.oc0) dB[0] = zp.B.x;
-                else if (c.oc1) dB[1] = zp.B.y;
-            }
+            const unsigned sf = c.sf;
+            if (sf & 1u) st2(dA, zp.A);
+            if (sf & 2u) dA[0] = zp.A.x;
+            if (sf & 4u) dA[1] = zp.A.y;
+            if (sf & 8u) st2(dB, zp.B);
+            if (sf & 16u) dB[0] = zp.B.x;
+            if (sf & 32u) dB[1] = zp.B.y;
         }
     }
     if (POST != POST_NONE && (FAST || p >= c.pb3)) {     // ---- residual at plane q = p-2 (fresidual3d, :300-323)
@@ -202,10 +206,11 @@ __device__ __forceinline__ void vleg_plane(const VlegCtx& c, int p, int t, const
         if (POST == POST_NORM) {
             if (FAST || q < c.k1) {     // fnorm, basicoperators.f90:422-440 (interior cells, msk = 1)
                 double a = 0.0;
-                if (c.orA && c.oc0) a = a + r0 * r0;
-                if (c.orA && c.oc1) a = a + r1 * r1;
-                if (c.orB && c.oc0) a = a + r2 * r2;
-                if (c.orB && c.oc1) a = a + r3 * r3;
+                const unsigned sf = c.sf;
+                if (sf & 64u) a = a + r0 * r0;
+                if (sf & 128u) a = a + r1 * r1;
+                if (sf & 256u) a = a + r2 * r2;
+                if (sf & 512u) a = a + r3 * r3;
                 acc = acc + a;
             }
         } else {
@@ -217,9 +222,7 @@ __device__ __forceinline__ void vleg_plane(const VlegCtx& c, int p, int t, const
                     rsum = r1 + r0n; rsum = rsum + r3; rsum = rsum + r2n;
                 } else {
                     rsum = rsum + r1; rsum = rsum + r0n; rsum = rsum + r3; rsum = rsum + r2n;
-                    if (c.orA && c.oc1)
-                        c.bc[(long long)(NH + ((q - 1 - NH) >> 1)) * c.gc.sk + (long long)(NH + ((c.ajA - NH) >> 1)) * c.gc.sj +
-                             (NH + ((c.ai + 1 - NH) >> 1))] = 0.5 * rsum;
+                    if (c.sf & 128u) c.bc[(unsigned)(NH + ((q - 1 - NH) >> 1)) * c.csk32 + c.bcA] = 0.5 * rsum;
                 }
             }
         }
@@ -290,23 +293,25 @@ k_vleg(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensor
 
     // first coarse column under the region; a box must start on a 16-byte boundary, i.e. on an even column
     const int CX0 = RX0 / 2 + 1;
-    // ---- producer state (thread 0 only): plane t of this chunk = array plane pl0 + t -> stage t % VL_S
-    int cnext = 0;
-    if (PRO) cnext = NH + ((pl0 - NH) >> 1) - 1;                         // first coarse plane needed
+    // ---- producer: plane t of this chunk = array plane pl0 + t -> stage t % VL_S.  Stateless (the coarse planes a
+    // fine plane brings along follow from t alone), so that the duty can rotate over the warps: whoever issues is
+    // late for the plane it is working on, and a fixed producer would hold up the block barrier of every plane.
+    const int cfirst = PRO ? NH + ((pl0 - NH) >> 1) - 1 : 0;            // first coarse plane needed
     auto issue = [&](int t) {
         const int f = pl0 + t, s = t & (VL_S - 1);
         uint32_t bytes = 2 * VL_PLANE * 8;
-        int mneed = -1;
+        int c_lo = 0, c_hi = -1;
         if (PRO) {
-            mneed = NH + ((f - NH) >> 1) + 1;
-            if (mneed >= cnext) bytes += (uint32_t)(mneed - cnext + 1) * VL_CBYTES;
+            c_hi = NH + ((f - NH) >> 1) + 1;
+            c_lo = t == 0 ? cfirst : NH + ((f - 1 - NH) >> 1) + 2;
+            if (c_hi >= c_lo) bytes += (uint32_t)(c_hi - c_lo + 1) * VL_CBYTES;
         }
         nytma::mbar_expect_tx(&full[s], bytes);
         nytma::load_3d(sx + s * VL_PLANE, &tmx, RX0, RY0, f, &full[s]);
         nytma::load_3d(sb + s * VL_PLANE, &tmb, RX0, RY0, f, &full[s]);
         if (PRO) {
-            for (; cnext <= mneed; cnext++)
-                nytma::load_3d(sc + (cnext % VL_SC) * VL_CSLOT, &tmc, CX0 & ~1, RY0 / 2 + 1, cnext, &full[s]);
+            for (int cp = c_lo; cp <= c_hi; cp++)
+                nytma::load_3d(sc + (cp % VL_SC) * VL_CSLOT, &tmc, CX0 & ~1, RY0 / 2 + 1, cp, &full[s]);
         }
         // the planes after the next ones are pulled into L2 meanwhile
         if (t + VL_L2AHEAD < nplanes) {
@@ -333,11 +338,28 @@ k_vleg(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensor
     c.cA0 = cnt_xy(g, ai, ajA); c.cA1 = cnt_xy(g, ai + 1, ajA); c.cB0 = cnt_xy(g, ai, ajB); c.cB1 = cnt_xy(g, ai + 1, ajB);
     c.rA0 = c.cA0 >= 0 ? 1.0 / (double)(c.cA0 + 2) : 0.0; c.rA1 = c.cA1 >= 0 ? 1.0 / (double)(c.cA1 + 2) : 0.0;
     c.rB0 = c.cB0 >= 0 ? 1.0 / (double)(c.cB0 + 2) : 0.0; c.rB1 = c.cB1 >= 0 ? 1.0 / (double)(c.cB1 + 2) : 0.0;
-    c.oc0 = e >= 3 && e < 3 + VL_TI && ai < g.nx + NH; c.oc1 = e + 1 >= 3 && e + 1 < 3 + VL_TI && ai + 1 < g.nx + NH;
-    c.orA = rA >= APT && rA < APT + TJ && ajA < g.ny + NH; c.orB = rA + 1 >= APT && rA + 1 < APT + TJ && ajB < g.ny + NH;
+    {
+        const bool oc0 = e >= 3 && e < 3 + VL_TI && ai < g.nx + NH, oc1 = e + 1 >= 3 && e + 1 < 3 + VL_TI && ai + 1 < g.nx + NH;
+        const bool orA = rA >= APT && rA < APT + TJ && ajA < g.ny + NH, orB = rA + 1 >= APT && rA + 1 < APT + TJ && ajB < g.ny + NH;
+        unsigned sf = 0;
+        if (orA) sf |= (oc0 && oc1) ? 1u : oc0 ? 2u : oc1 ? 4u : 0u;
+        if (orB) sf |= (oc0 && oc1) ? 8u : oc0 ? 16u : oc1 ? 32u : 0u;
+        if (orA && oc0) sf |= 64u;
+        if (orA && oc1) sf |= 128u;
+        if (orB && oc0) sf |= 256u;
+        if (orB && oc1) sf |= 512u;
+        unsigned gA = (unsigned)((long long)ajA * g.sj + ai), bcA = 0;
+        // the coarse cell under columns (e+1, e+2) and rows (A, B); only threads with bit 7 set ever use it
+        if (POST == POST_RESTRICT && (sf & 128u))
+            bcA = (unsigned)((long long)(NH + ((ajA - NH) >> 1)) * gc.sj + (NH + ((ai + 1 - NH) >> 1)));
+        asm volatile("mov.b32 %0, %0;" : "+r"(sf));
+        asm volatile("mov.b32 %0, %0;" : "+r"(gA));
+        asm volatile("mov.b32 %0, %0;" : "+r"(bcA));
+        c.sf = sf; c.gA = gA; c.bcA = bcA;
+        c.sk32 = (unsigned)g.sk; c.csk32 = (unsigned)gc.sk;
+    }
     c.oA = rA * VL_RI + e;
     c.oUp = (rA > 0 ? rA - 1 : 0) * VL_RI + e; c.oDn = (rA + 2 < VL_RJ ? rA + 2 : VL_RJ - 1) * VL_RI + e;
-    c.gA = (long long)ajA * g.sj + ai;
     c.exA0 = c.exA1 = c.exB0 = c.exB1 = 0;
     if (PRO) {
         // coarse tile rows (warp, warp+1) x columns (lane, lane+1); in-domain flags of the "other" coarse
@@ -366,7 +388,7 @@ k_vleg(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensor
         const int t = p - pstart;                                                                                   \
         nytma::mbar_wait(&full[t & (VL_S - 1)], (uint32_t)(t / VL_S) & 1u);                                         \
         __syncthreads(); /* plane t landed; everything written in the last iteration is visible */                  \
-        if (threadIdx.x == 0 && t + 2 < nplanes) issue(t + 2);                                                      \
+        if (lane == 0 && warp == (t & (VL_NW - 1)) && t + 2 < nplanes) issue(t + 2);                                \
         if (p >= fast_lo && p <= fast_hi)                                                                           \
             vleg_plane<PRO, POST, true, INT>(c, p, t, X##m, X##c_, X##n, Y##m, Y##c_, Y##n, Z##m, Z##c_, Z##n, B##n, B##c_, B##m, acc, rsum); \
         else                                                                                                        \

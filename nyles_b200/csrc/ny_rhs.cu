@@ -6,7 +6,9 @@
 // evaluated per cell so that all global loads are coalesced along i whatever the sweep axis.
 // Accumulation order per output cell equals the order of the reference's passes.
 #include "ny_common.cuh"
+#include <cstdlib>
 #include "ny_weno.cuh"
+#include "ny_tma.cuh"
 
 namespace {
 
@@ -229,26 +231,33 @@ __device__ __forceinline__ void momentum_cell(
 #ifndef MOM_MINB
 #define MOM_MINB 5
 #endif
+// the box of cells [i0,i1) x [j0,j1) x [k0,k1) a launch of k_momentum covers (the whole array, or one of the six
+// slabs of the 3-cell frame around the cells that k_mom3 computes)
+struct CellBox { int i0, i1, j0, j1, k0, k1; };
+
 template <bool FAST, bool ACCUM, bool VORTEX, bool BERN>
 __global__ void __launch_bounds__(256, MOM_MINB)
 k_momentum(const double* __restrict__ Ux, const double* __restrict__ Uy, const double* __restrict__ Uz,
            const double* __restrict__ wx, const double* __restrict__ wy, const double* __restrict__ wz,
            const double* __restrict__ ke, const double* __restrict__ b,
            double* __restrict__ dux, double* __restrict__ duy, double* __restrict__ duz,
-           double cff, int with_b, Ext e, TsUpd upd)
+           double cff, int with_b, Ext e, TsUpd upd, CellBox cb)
 {
-    const int i0 = blockIdx.x * blockDim.x, j0 = blockIdx.y * blockDim.y, k0 = blockIdx.z * blockDim.z;
+    const int i0 = cb.i0 + blockIdx.x * blockDim.x, j0 = cb.j0 + blockIdx.y * blockDim.y, k0 = cb.k0 + blockIdx.z * blockDim.z;
     const int i = i0 + threadIdx.x, j = j0 + threadIdx.y, k = k0 + threadIdx.z;
     // CTA-uniform: every cell of the tile has all six sweeps in the interior range of flux1d
     const bool interior = VORTEX && i0 >= 3 && i0 + (int)blockDim.x - 1 <= e.nx - 4 && j0 >= 3 &&
-                          j0 + (int)blockDim.y - 1 <= e.ny - 4 && k0 >= 3 && k0 + (int)blockDim.z - 1 <= e.nz - 4;
+                          j0 + (int)blockDim.y - 1 <= e.ny - 4 && k0 >= 3 && k0 + (int)blockDim.z - 1 <= e.nz - 4 &&
+                          i0 + (int)blockDim.x <= cb.i1 && j0 + (int)blockDim.y <= cb.j1 && k0 + (int)blockDim.z <= cb.k1;
     if (interior) {
         momentum_cell<FAST, VORTEX, ACCUM, VORTEX, BERN>(Ux, Uy, Uz, wx, wy, wz, ke, b, dux, duy, duz, cff, with_b, e, i, j, k, upd);
         return;
     }
-    if (i >= e.nx || j >= e.ny || k >= e.nz) return;
+    if (i >= cb.i1 || j >= cb.j1 || k >= cb.k1) return;
     momentum_cell<FAST, false, ACCUM, VORTEX, BERN>(Ux, Uy, Uz, wx, wy, wz, ke, b, dux, duy, duz, cff, with_b, e, i, j, k, upd);
 }
+
+#include "ny_mom3.cuh"
 
 __global__ void __launch_bounds__(256)
 k_add_laplacian(const double* __restrict__ phi, double* __restrict__ dphi, double cx, double cy, double cz, Ext e)
@@ -335,16 +344,76 @@ static int launch_momentum(ny_ctx* ctx, const double* Ux, const double* Uy, cons
     TsUpd upd;
     memset(&upd, 0, sizeof(upd));
     if (updp) upd = *updp;
-    ny_grid3 g = ny_cells_launch(e.nz, e.ny, e.nx);
     ny_prof_scope ps(ctx, NY_PROF_RHS_MOMENTUM, st);
-    if (ctx->fast_arith && VORTEX)
-        k_momentum<true, ACCUM, VORTEX, BERN><<<g.grid, g.block, 0, st>>>(Ux, Uy, Uz, wx, wy, wz, ke, b, dux, duy, duz,
-                                                                          cff, with_b, make_ext(e), upd);
-    else
-        k_momentum<false, ACCUM, VORTEX, BERN><<<g.grid, g.block, 0, st>>>(Ux, Uy, Uz, wx, wy, wz, ke, b, dux, duy, duz,
-                                                                           cff, with_b, make_ext(e), upd);
-    NY_CHECK_LAUNCH(ctx);
-    return NY_OK;
+    // one launch of the cell-parallel kernel over a box of cells, with a block shape that suits the box
+    auto launch_box = [&](CellBox cb, dim3 block) -> int {
+        if (cb.i0 >= cb.i1 || cb.j0 >= cb.j1 || cb.k0 >= cb.k1) return NY_OK;
+        dim3 grid((cb.i1 - cb.i0 + block.x - 1) / block.x, (cb.j1 - cb.j0 + block.y - 1) / block.y,
+                  (cb.k1 - cb.k0 + block.z - 1) / block.z);
+        if (ctx->fast_arith && VORTEX)
+            k_momentum<true, ACCUM, VORTEX, BERN><<<grid, block, 0, st>>>(Ux, Uy, Uz, wx, wy, wz, ke, b, dux, duy, duz, cff,
+                                                                          with_b, make_ext(e), upd, cb);
+        else
+            k_momentum<false, ACCUM, VORTEX, BERN><<<grid, block, 0, st>>>(Ux, Uy, Uz, wx, wy, wz, ke, b, dux, duy, duz, cff,
+                                                                           with_b, make_ext(e), upd, cb);
+        NY_CHECK_LAUNCH(ctx);
+        return NY_OK;
+    };
+    // The cells whose six sweeps are all in the interior range of flux1d go to the plane-marching TMA kernel
+    // (ny_mom3.cuh); k_momentum keeps the 3-cell frame around them.  TMA needs an even row length and 16-byte
+    // aligned arrays; small grids stay on one launch (mom_variant: 0 = by size, 1 = always k_momentum, 2 = k_mom3
+    // wherever it is legal).
+    const bool fused = VORTEX && BERN && !ACCUM;
+    const long long cells = (long long)e.nx * e.ny * e.nz;
+    bool use3 = fused && ctx->mom_variant != 1 && (ctx->mom_variant == 2 || cells >= (1LL << 18)) && (e.nx & 1) == 0 &&
+                e.nx >= 7 && e.ny >= 7 && e.nz >= 7;
+    if (use3) {
+        const void* ptrs[] = {Ux, Uy, Uz, wx, wy, wz, ke, with_b ? b : ke};
+        for (const void* p : ptrs) use3 = use3 && (reinterpret_cast<uintptr_t>(p) & 15) == 0;
+    }
+    if (!use3) return launch_box({0, e.nx, 0, e.ny, 0, e.nz}, dim3(32, 4, 2));
+    {
+        using namespace m3;
+        Maps tm;
+        int r = ny_tma_encode_3d(&tm.wz, wz, e.nx, e.ny, e.nz, PW, TY + 6, 1);
+        if (r == NY_OK) r = ny_tma_encode_3d(&tm.wx, wx, e.nx, e.ny, e.nz, PN, TY + 6, 1);
+        if (r == NY_OK) r = ny_tma_encode_3d(&tm.wy, wy, e.nx, e.ny, e.nz, PW, TY, 1);
+        if (r == NY_OK) r = ny_tma_encode_3d(&tm.Ux, Ux, e.nx, e.ny, e.nz, PN, TY + 1, 1);
+        if (r == NY_OK) r = ny_tma_encode_3d(&tm.Uy, Uy, e.nx, e.ny, e.nz, PN, TY + 1, 1);
+        if (r == NY_OK) r = ny_tma_encode_3d(&tm.Uz, Uz, e.nx, e.ny, e.nz, PN, TY + 1, 1);
+        if (r == NY_OK) r = ny_tma_encode_3d(&tm.ke, ke, e.nx, e.ny, e.nz, PN, TY + 1, 1);
+        if (r == NY_OK) r = ny_tma_encode_3d(&tm.b, with_b ? b : ke, e.nx, e.ny, e.nz, PN, TY, 1);
+        if (r != NY_OK) return r;
+        const int ni = e.nx - 6, nj = e.ny - 6, nk = e.nz - 6;
+        const int gx = (ni + TX - 1) / TX, gy = (nj + TY - 1) / TY;
+        // Chunks of planes.  A chunk re-reads two planes and refills its queues, so chunks should not be short; but the
+        // last CTAs of an SM run below full occupancy for about half a chunk, so they should not be long either
+        // (measured at 512^3: 169 planes per chunk 6.2 ms, 127 planes 5.5 ms; profiles/r2_b_*).
+        int kchunk = 32;
+        { const char* v = getenv("NY_MOM3_KCHUNK"); if (v && atoi(v) > 0) kchunk = atoi(v); }
+        if (kchunk > nk) kchunk = nk;
+        dim3 grid(gx, gy, (nk + kchunk - 1) / kchunk);
+        static bool attr_set[2] = {false, false};
+        const int fa = ctx->fast_arith ? 1 : 0;
+        if (!attr_set[fa]) {
+            cudaError_t ce = fa ? cudaFuncSetAttribute(k_mom3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)
+                                : cudaFuncSetAttribute(k_mom3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+            if (ce != cudaSuccess) { ny_set_error("k_mom3: cannot reserve %d bytes of shared memory", SMEM); return NY_ERR_CUDA; }
+            attr_set[fa] = true;
+        }
+        if (fa) k_mom3<true><<<grid, TX * TY, SMEM, st>>>(tm, Uz, wx, wy, dux, duy, duz, cff, with_b, make_ext(e), kchunk, upd);
+        else k_mom3<false><<<grid, TX * TY, SMEM, st>>>(tm, Uz, wx, wy, dux, duy, duz, cff, with_b, make_ext(e), kchunk, upd);
+        NY_CHECK_LAUNCH(ctx);
+    }
+    // the frame: two z slabs over the whole plane, two y slabs between them, two x slabs between those
+    const int x1 = e.nx - 3, y1 = e.ny - 3, z1 = e.nz - 3;
+    int r = launch_box({0, e.nx, 0, e.ny, 0, 3}, dim3(32, 8, 1));
+    if (r == NY_OK) r = launch_box({0, e.nx, 0, e.ny, z1, e.nz}, dim3(32, 8, 1));
+    if (r == NY_OK) r = launch_box({0, e.nx, 0, 3, 3, z1}, dim3(32, 1, 8));
+    if (r == NY_OK) r = launch_box({0, e.nx, y1, e.ny, 3, z1}, dim3(32, 1, 8));
+    if (r == NY_OK) r = launch_box({0, 3, 3, y1, 3, z1}, dim3(4, 8, 8));
+    if (r == NY_OK) r = launch_box({x1, e.nx, 3, y1, 3, z1}, dim3(4, 8, 8));
+    return r;
 }
 
 extern "C" int ny_set_arith(ny_ctx* ctx, int fast)
@@ -354,6 +423,13 @@ extern "C" int ny_set_arith(ny_ctx* ctx, int fast)
     return NY_OK;
 }
 extern "C" int ny_get_arith(ny_ctx* ctx) { return ctx ? ctx->fast_arith : 0; }
+
+extern "C" int ny_set_momentum_variant(ny_ctx* ctx, int variant)
+{
+    NY_REQUIRE(ctx && variant >= 0 && variant <= 2, "bad argument");
+    ctx->mom_variant = variant;
+    return NY_OK;
+}
 
 extern "C" int ny_debug_weno5(ny_ctx* ctx, const double* q, double* out, long long n, void* stream)
 {

@@ -48,6 +48,7 @@ _PROTOS = {
     "ny_prof_name": ([_I], C.c_char_p),
     "ny_set_arith": ([_P, _I], _I),
     "ny_get_arith": ([_P], _I),
+    "ny_set_momentum_variant": ([_P, _I], _I),
     "ny_vorticity": ([_P] + [_P] * 6 + [ny_ext, _D, _P], _I),
     "ny_upwind": ([_P] + [_P] * 5 + [ny_ext, _P], _I),
     "ny_upwind_diff": ([_P] + [_P] * 5 + [_D, _D, _D, ny_ext, _P], _I),

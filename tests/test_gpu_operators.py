@@ -193,9 +193,18 @@ def test_vortex_force_and_bernoulli(K, L, shape):
             assert np.array_equal(a, host(t))
 
 
-@pytest.mark.parametrize("shape", SHAPES[1:])
+@pytest.fixture(params=[1, 2], ids=["cellwise", "tma_marching"])
+def mom_variant(request, L):
+    """Which kernel evaluates the interior cells of the fused momentum right-hand side: k_momentum (one thread per
+    cell) or k_mom3 (plane marching, TMA-staged tiles; needs an even nx).  Both must be bit-identical."""
+    L.check(L.load().ny_set_momentum_variant(L.context(), request.param))
+    yield request.param
+    L.check(L.load().ny_set_momentum_variant(L.context(), 0))
+
+
+@pytest.mark.parametrize("shape", SHAPES[1:] + [(40, 37, 70), (9, 70, 34)])
 @pytest.mark.parametrize("flags", [0, 1, 2])
-def test_fused_rhs_equals_operator_sequence(K, L, shape, flags):
+def test_fused_rhs_equals_operator_sequence(K, L, shape, flags, mom_variant):
     euler, linear = flags & 1, flags & 2
     b, ke = rand_fields(shape, 2, 30)
     U = rand_fields(shape, 3, 31)
@@ -225,13 +234,13 @@ def test_fused_rhs_equals_operator_sequence(K, L, shape, flags):
 @pytest.mark.parametrize("mode", [1, 2, 3])
 @pytest.mark.parametrize("flags", [0, 1, 2])
 @pytest.mark.parametrize("forced", [False, True])
-def test_rhs_step_equals_rhs_then_timescheme(L, shape, mode, flags, forced):
+def test_rhs_step_equals_rhs_then_timescheme(L, shape, mode, flags, forced, mom_variant):
     """ny_rhs_step (the RHS kernels apply the LFAM3 / Euler update and write each field once, into a
     separate buffer) against ny_rhs followed by the ny_ts_* kernels: bit-identical new state, and none
     of the arrays it only reads is touched.  forced: user tendencies (what a forcing object adds to dstate after
     the RHS, core/model_les.py:143-144) for b and two of the velocity components."""
     euler = flags & 1
-    if forced and shape != SHAPES[1]:
+    if forced and shape != SHAPES[2]:
         pytest.skip("user tendencies are exercised on one shape")
     b, ke, sb_b, sn_b = rand_fields(shape, 4, 40)
     U, w, u, ub, un = (rand_fields(shape, 3, 41 + n) for n in range(5))

@@ -71,11 +71,13 @@ def main():
     ap.add_argument("--fast", type=int, default=0)
     ap.add_argument("--what", default="rhs,mg")
     ap.add_argument("--sustained", type=int, default=0)
+    ap.add_argument("--mom", type=int, default=0, help="momentum kernel variant (ny_set_momentum_variant)")
     a = ap.parse_args()
     n = a.n
     L = lib.load()
     ctx = lib.context()
     lib.set_arith(bool(a.fast))
+    lib.check(L.ny_set_momentum_variant(ctx, a.mom))
     dev = "cuda"
     cells = n ** 3
     st = lib.stream()
@@ -103,8 +105,8 @@ def main():
             t_rhs = timeit(lambda: lib.check(L.ny_rhs(ctx, lib.ptr(b), lib.ptr(Ux), lib.ptr(Uy), lib.ptr(Uz), lib.ptr(wx), lib.ptr(wy),
                                                       lib.ptr(wz), lib.ptr(ke), lib.ptr(out[0]), lib.ptr(out[1]), lib.ptr(out[2]),
                                                       lib.ptr(out[3]), 0.25, 0, e, st)))
-            print("rhs %-9s fast=%d n=%d: tracer %.3f ms (%.0f GB/s alg), momentum %.3f ms (%.0f GB/s alg)"
-                  % (label, a.fast, n, t_tr, 40 * cells / t_tr / 1e6, t_rhs - t_tr, 88 * cells / (t_rhs - t_tr) / 1e6), flush=True)
+            print("rhs %-9s fast=%d mom=%d n=%d: tracer %.3f ms (%.0f GB/s alg), momentum %.3f ms (%.0f GB/s alg)"
+                  % (label, a.fast, a.mom, n, t_tr, 40 * cells / t_tr / 1e6, t_rhs - t_tr, 88 * cells / (t_rhs - t_tr) / 1e6), flush=True)
             if a.sustained:
                 t, c = sustained(lambda: lib.check(L.ny_upwind(ctx, lib.ptr(b), lib.ptr(Ux), lib.ptr(Uy), lib.ptr(Uz), lib.ptr(out[0]), e, st)))
                 print("   sustained tracer %.3f ms, %s" % (t, c), flush=True)
