@@ -290,18 +290,26 @@ def family_bytes_per_cell(euler):
     }
 
 
-# fp64 instructions (DADD+DMUL+DFMA+DSETP) per cell in the interior path of the strict kernels, from cuobjdump -sass
-DP_INSTR_PER_CELL = {"rhs_momentum": 633.0, "rhs_tracer": 321.0}
-# dram__bytes_read.sum + dram__bytes_write.sum per launch group from `ncu --set full` of this same command
-# (tools/ncu_traffic.py writes the map; the capture itself is never a bench value)
-def traffic_from_ncu():
+# dram bytes and executed fp64 instructions per launch group, from the `ncu --set full` capture of this same command
+# (tools/ncu_traffic.py writes the map; the capture itself is never a bench value).  The map carries a hash of the
+# kernel sources it was taken from: numbers of another build are reported as stale, not silently quoted.
+def ncu_facts():
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    try:
+        from ncu_traffic import source_stamp
+        stamp = source_stamp()
+    except Exception:                     # noqa: BLE001
+        stamp = None
     for path in (os.path.join(ROOT, "gpurun_out", "ncu_traffic.json"), os.path.join(ROOT, "profiles", "ncu_traffic.json")):
         try:
             with open(path) as f:
-                return json.load(f).get("families", {})
+                d = json.load(f)
         except (OSError, ValueError):
             continue
-    return {}
+        d["stale"] = not (stamp is not None and d.get("stamp") == stamp)
+        d["path"] = os.path.relpath(path, ROOT)
+        return d
+    return {"families": {}, "fp64": {}, "stale": True, "path": None}
 
 
 def comm_stats(steps):
@@ -460,6 +468,14 @@ def run_ours(args):
     peak_gbs, peak_src = (peaks["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured copy)") if "hbm_gbs" in peaks \
         else (6650.0, "fallback of B200_PROFILING.md")
     fam = family_bytes_per_cell(euler)
+    facts = ncu_facts()
+    fp64_peak = None
+    try:                                   # ~0.5 s of DFMA-only launches: what the fp64 pipe sustains on this board
+        out = lib.C.c_double()
+        lib.check(lib.load().ny_debug_fp64_peak(lib.context(), 0.5, lib.C.byref(out), lib.stream()))
+        fp64_peak = out.value * 32.0        # thread-level instructions per second
+    except Exception as exc:               # noqa: BLE001
+        print("fp64 peak measurement failed: %r" % (exc,), file=sys.stderr)
     local_cells = cells / world
     timed = {k: v for k, v in prof.items() if v[1] > 0}
     total_ms = sum(v[0] for v in timed.values())
@@ -469,17 +485,25 @@ def run_ours(args):
         t_ms, n = timed[top]
         achieved = fam[top] * local_cells / (t_ms / n * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                    "frac": achieved / peak_gbs, "traffic": traffic_from_ncu().get(top), "peak_source": peak_src,
+                    "frac": achieved / peak_gbs, "traffic": None if facts["stale"] else facts.get("families", {}).get(top),
+                    "traffic_source": ("%s%s" % (facts["path"], " (STALE: taken from other kernel sources)" if facts["stale"] else ""))
+                    if facts["path"] else None,
+                    "peak_source": peak_src,
                     "algorithmic_bytes_per_cell": fam[top], "launch_groups": n, "avg_ms": t_ms / n,
                     "share_of_step": t_ms / ms}
-        if top in DP_INSTR_PER_CELL and not args.fast_arith:
-            # the WENO kernels are bound by the fp64 pipe, not by HBM: fp64 instructions per cell counted in
-            # the SASS of the interior path against 64 fp64 lanes per SM per clock
-            rate = DP_INSTR_PER_CELL[top] * local_cells / (t_ms / n * 1e-3)
-            peak_dp = 148 * 64 * 1.965e9
-            roofline["fp64_pipe"] = {"dp_instr_per_cell": DP_INSTR_PER_CELL[top], "achieved_instr_per_s": rate,
-                                     "peak_instr_per_s": peak_dp, "frac": rate / peak_dp,
-                                     "note": "actual limiter of this kernel; the hbm fraction above is low by construction"}
+        f64 = facts.get("fp64", {}).get(top)
+        if f64 and not facts["stale"] and not args.fast_arith:
+            # the WENO kernels are bound by the fp64 pipe (and by the power it draws), not by HBM: executed fp64
+            # instructions per cell from the ncu capture against the DFMA-only rate this board sustains under its
+            # power cap (ny_debug_fp64_peak, measured below) and against 64 lanes per SM per clock at the maximum clock
+            rate = f64["dp_instr_per_cell"] * local_cells / (t_ms / n * 1e-3)
+            roofline["fp64_pipe"] = {"dp_instr_per_cell": f64["dp_instr_per_cell"], "achieved_instr_per_s": rate,
+                                     "peak_instr_per_s_sustained_measured": fp64_peak,
+                                     "frac_of_sustained_measured": rate / fp64_peak if fp64_peak else None,
+                                     "peak_instr_per_s_nominal": 148 * 64 * 1.965e9, "frac_of_nominal": rate / (148 * 64 * 1.965e9),
+                                     "ncu_pipe_fp64_pct_isolated_launch": f64["ncu_pipe_fp64_pct"],
+                                     "note": "actual limiter of this kernel (with the 1 kW power cap); the hbm fraction "
+                                             "above is low by construction"}
     else:
         roofline = None
     B = bytes_per_cell_step(w, n_vc)

@@ -98,10 +98,12 @@ const char* ny_prof_name(int tag);
  * Differences are a few ulp, far inside the 1e-12 parity bar (tests/test_gpu_operators.py). */
 int  ny_set_arith(ny_ctx* ctx, int fast);
 int  ny_get_arith(ny_ctx* ctx);
-/* Which kernel evaluates the fused momentum right-hand side on the cells whose six WENO sweeps are interior
- * (3 <= s <= n-4 on every axis): 0 (default) = the plane-marching TMA kernel for grids of at least 2^18 cells,
- * the cell-parallel kernel below that; 1 = always the cell-parallel kernel; 2 = the TMA kernel wherever it is
- * legal (even nx, 16-byte aligned arrays).  Both are bit-identical; the switch exists for tests and timing. */
+/* Which kernels evaluate the WENO right-hand sides.  0 (default): the momentum equations run the plane-marching
+ * TMA kernel (k_mom3) on the cells whose six sweeps are interior (3 <= s <= n-4 on every axis) for grids of at least
+ * 2^18 cells and the cell-parallel kernel on the 3-cell frame and on small grids; the tracer runs the cell-parallel
+ * kernel.  1 = cell-parallel kernels only.  2 = the plane-marching TMA kernels (k_mom3, k_up3) wherever they are
+ * legal (even nx, 16-byte aligned arrays), whatever the size.  All variants are bit-identical; the switch exists for
+ * tests and timing. */
 int  ny_set_momentum_variant(ny_ctx* ctx, int variant);
 
 /* ---- f2py kernel replacements ------------------------------------------------------ */
@@ -305,6 +307,9 @@ int  ny_mg_op(ny_mg*, int op, int lev, void* stream);
  * receives the number of t for which it differs (bitwise) from the IEEE quotient. */
 int  ny_debug_weno5(ny_ctx*, const double* q, double* out, long long n, void* stream);
 int  ny_debug_weno3(ny_ctx*, const double* q, double* out, long long n, void* stream);
+/* measurement aid: sustained issue rate of the fp64 pipe (DFMA only, ~`seconds` of back-to-back launches under the
+ * board's power cap), in warp-wide fp64 instructions per second over the whole device; synchronises `stream` */
+int  ny_debug_fp64_peak(ny_ctx*, double seconds, double* dp_warp_instr_per_s, void* stream);
 int  ny_debug_div(ny_ctx*, const double* a, const double* b, double* out, long long n,
                   long long* mismatch_host, void* stream);
 

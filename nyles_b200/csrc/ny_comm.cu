@@ -172,7 +172,8 @@ int ny_comm_allgather_inplace(ny_comm* c, double* d_recv, size_t count_per_rank,
 // what NVLink 5 carries, and every group is a rendezvous of both ranks inside NCCL.  Here a rank PUSHES its
 // boundary planes straight into a receive slot in the neighbour's memory (IPC-mapped, plain 16-byte
 // stores over NVLink from a grid of CTAs), raises a flag there once all its stores are globally visible,
-// then waits for the flag the neighbour raises in ITS slot and copies the planes into its halo.
+// then waits for the flag the neighbour raises in ITS slot and copies the planes into its halo -- all in one
+// launch (k_p2p_exchange).
 // Slot reuse needs no acknowledgement: exchanges are issued in the same order on every rank and a rank
 // cannot run more than one exchange ahead of a neighbour whose data it waits for, so with
 // NY_P2P_SLOTS >= 2 (4 here: one exchange may be in flight on the overlap stream as well) a slot is never
@@ -204,47 +205,49 @@ __device__ __forceinline__ void p2p_copy(const P2PSeg& s, long long first, long 
     }
 }
 
+__device__ __forceinline__ void p2p_wait_flags(const P2PArgs& a)
+{
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (int d = 0; d < 2; d++) {
+        if (!a.flag[d]) continue;
+        const volatile unsigned long long* f = a.flag[d];
+        while (*f < a.seq) {
+            __nanosleep(100);
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 60000000000ull) {     // a neighbour died: fail loudly instead of hanging the GPU
+                printf("libnyles_b200: halo exchange %llu timed out waiting for a slab neighbour\n", a.seq);
+                __trap();
+            }
+        }
+    }
+    __threadfence_system();
+}
+
+// ONE launch per exchange: every CTA pushes its share of the boundary planes into the neighbours' slots; the last
+// one to finish raises the arrival flags over there; then every CTA waits for the flags the neighbours raise HERE
+// and unpacks its share of the received planes into the halo.  The grid is never larger than what is resident at
+// once (2 CTAs of 512 threads per SM), so CTAs that spin on a flag cannot keep CTAs that still have to push off the
+// machine.
 __global__ void __launch_bounds__(512)
-k_p2p_push(P2PArgs a)
+k_p2p_exchange(P2PArgs push, P2PArgs pull)
 {
     const long long first = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
-    for (int s = 0; s < a.nseg; s++) p2p_copy(a.seg[s], first, stride);
+    for (int s = 0; s < push.nseg; s++) p2p_copy(push.seg[s], first, stride);
     __threadfence_system();                         // my stores are visible to the neighbour's GPU ...
     __syncthreads();
     if (threadIdx.x == 0) {
-        const unsigned int done = atomicAdd(a.counter, 1u);
+        const unsigned int done = atomicAdd(push.counter, 1u);
         if (done == gridDim.x - 1) {                // ... and so are those of every other CTA: raise the flags
-            *a.counter = 0u;
+            *push.counter = 0u;
             __threadfence_system();
-            if (a.flag[0]) *reinterpret_cast<volatile unsigned long long*>(a.flag[0]) = a.seq;
-            if (a.flag[1]) *reinterpret_cast<volatile unsigned long long*>(a.flag[1]) = a.seq;
+            if (push.flag[0]) *reinterpret_cast<volatile unsigned long long*>(push.flag[0]) = push.seq;
+            if (push.flag[1]) *reinterpret_cast<volatile unsigned long long*>(push.flag[1]) = push.seq;
         }
-    }
-}
-
-__global__ void __launch_bounds__(256)
-k_p2p_wait_unpack(P2PArgs a)
-{
-    if (threadIdx.x == 0) {
-        unsigned long long t0, t1;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-        for (int d = 0; d < 2; d++) {
-            if (!a.flag[d]) continue;
-            const volatile unsigned long long* f = a.flag[d];
-            while (*f < a.seq) {
-                __nanosleep(200);
-                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-                if (t1 - t0 > 60000000000ull) {     // a neighbour died: fail loudly instead of hanging the GPU
-                    printf("libnyles_b200: halo exchange %llu timed out waiting for a slab neighbour\n", a.seq);
-                    __trap();
-                }
-            }
-        }
-        __threadfence_system();
+        p2p_wait_flags(pull);
     }
     __syncthreads();
-    const long long first = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
-    for (int s = 0; s < a.nseg; s++) p2p_copy(a.seg[s], first, stride);
+    for (int s = 0; s < pull.nseg; s++) p2p_copy(pull.seg[s], first, stride);
 }
 
 static void p2p_release(ny_comm* c)
@@ -371,10 +374,7 @@ static int p2p_exchange(ny_comm* c, double* const* arrays, const size_t* plane, 
     const int sms = c->ctx->num_sms > 0 ? c->ctx->num_sms : 148;
     int nblk = (int)(moved >> 16);                  // one CTA per 64 KiB, 4 .. 2 per SM
     nblk = nblk < 4 ? 4 : (nblk > 2 * sms ? 2 * sms : nblk);
-    k_p2p_push<<<nblk, 512, 0, st>>>(push);
-    NY_CHECK_LAUNCH(c->ctx);
-    int nblk2 = nblk < 2 * sms ? nblk : 2 * sms;    // every CTA of the unpack polls the arrival flags first
-    k_p2p_wait_unpack<<<nblk2, 256, 0, st>>>(pull);
+    k_p2p_exchange<<<nblk, 512, 0, st>>>(push, pull);
     NY_CHECK_LAUNCH(c->ctx);
     *done = true;
     return NY_OK;

@@ -46,8 +46,12 @@ template <bool FAST>
 __device__ __forceinline__ double flux_smem(double u, const double* P, int s)
 {
     const bool up = u > 0.0;
-    const double* C = P + (up ? -s : 0);
-    const int t = up ? s : -s;
+    int t = up ? s : -s, o = up ? -s : 0;
+    // The step is made opaque to the compiler.  With a literal stride of 1, nvcc 12.9 turns the five indexed loads into
+    // loads of both candidates plus selects and gets one select wrong (C[t] read C[+1] for t = -1: measured in
+    // k_up3, tools/dbg_up3c.py); a step it cannot see through is a plain register offset.
+    asm volatile("" : "+r"(t), "+r"(o));
+    const double* C = P + o;
     return u * nyw::weno5<FAST>(C[-2 * t], C[-t], C[0], C[t], C[2 * t]);
 }
 }  // namespace m3

@@ -231,9 +231,11 @@ __device__ __forceinline__ void momentum_cell(
 #ifndef MOM_MINB
 #define MOM_MINB 5
 #endif
-// the box of cells [i0,i1) x [j0,j1) x [k0,k1) a launch of k_momentum covers (the whole array, or one of the six
-// slabs of the 3-cell frame around the cells that k_mom3 computes)
-struct CellBox { int i0, i1, j0, j1, k0, k1; };
+// The boxes of cells [i0,i1) x [j0,j1) x [k0,k1) that ONE launch of k_momentum covers: the whole array, or the six
+// slabs of the 3-cell frame around the cells that k_mom3 computes.  Each box has its own block shape (bx, by, bz),
+// 256 threads, and its own grid (gx, gy, .) of CTAs; the CTAs of all boxes are enumerated along blockIdx.x.
+struct CellBox { int i0, i1, j0, j1, k0, k1, bx, by, bz, gx, gy, start; };
+struct CellBoxes { int n, total; CellBox box[6]; };
 
 template <bool FAST, bool ACCUM, bool VORTEX, bool BERN>
 __global__ void __launch_bounds__(256, MOM_MINB)
@@ -241,14 +243,20 @@ k_momentum(const double* __restrict__ Ux, const double* __restrict__ Uy, const d
            const double* __restrict__ wx, const double* __restrict__ wy, const double* __restrict__ wz,
            const double* __restrict__ ke, const double* __restrict__ b,
            double* __restrict__ dux, double* __restrict__ duy, double* __restrict__ duz,
-           double cff, int with_b, Ext e, TsUpd upd, CellBox cb)
+           double cff, int with_b, Ext e, TsUpd upd, const __grid_constant__ CellBoxes boxes)
 {
-    const int i0 = cb.i0 + blockIdx.x * blockDim.x, j0 = cb.j0 + blockIdx.y * blockDim.y, k0 = cb.k0 + blockIdx.z * blockDim.z;
-    const int i = i0 + threadIdx.x, j = j0 + threadIdx.y, k = k0 + threadIdx.z;
+    int nb = 0;
+    while (nb + 1 < boxes.n && (int)blockIdx.x >= boxes.box[nb + 1].start) nb++;
+    const CellBox& cb = boxes.box[nb];
+    const int local = (int)blockIdx.x - cb.start;
+    const int cx = local % cb.gx, cy = (local / cb.gx) % cb.gy, cz = local / (cb.gx * cb.gy);
+    const int tid = threadIdx.x, tx = tid % cb.bx, ty = (tid / cb.bx) % cb.by, tz = tid / (cb.bx * cb.by);
+    const int i0 = cb.i0 + cx * cb.bx, j0 = cb.j0 + cy * cb.by, k0 = cb.k0 + cz * cb.bz;
+    const int i = i0 + tx, j = j0 + ty, k = k0 + tz;
     // CTA-uniform: every cell of the tile has all six sweeps in the interior range of flux1d
-    const bool interior = VORTEX && i0 >= 3 && i0 + (int)blockDim.x - 1 <= e.nx - 4 && j0 >= 3 &&
-                          j0 + (int)blockDim.y - 1 <= e.ny - 4 && k0 >= 3 && k0 + (int)blockDim.z - 1 <= e.nz - 4 &&
-                          i0 + (int)blockDim.x <= cb.i1 && j0 + (int)blockDim.y <= cb.j1 && k0 + (int)blockDim.z <= cb.k1;
+    const bool interior = VORTEX && i0 >= 3 && i0 + cb.bx - 1 <= e.nx - 4 && j0 >= 3 && j0 + cb.by - 1 <= e.ny - 4 &&
+                          k0 >= 3 && k0 + cb.bz - 1 <= e.nz - 4 && i0 + cb.bx <= cb.i1 && j0 + cb.by <= cb.j1 &&
+                          k0 + cb.bz <= cb.k1;
     if (interior) {
         momentum_cell<FAST, VORTEX, ACCUM, VORTEX, BERN>(Ux, Uy, Uz, wx, wy, wz, ke, b, dux, duy, duz, cff, with_b, e, i, j, k, upd);
         return;
@@ -258,6 +266,7 @@ k_momentum(const double* __restrict__ Ux, const double* __restrict__ Uy, const d
 }
 
 #include "ny_mom3.cuh"
+#include "ny_up3.cuh"
 
 __global__ void __launch_bounds__(256)
 k_add_laplacian(const double* __restrict__ phi, double* __restrict__ dphi, double cx, double cy, double cz, Ext e)
@@ -282,6 +291,23 @@ k_debug_weno5(const double* __restrict__ q, double* __restrict__ out, long long 
     if (t >= n) return;
     const double a = q[t], b = q[n + t], c = q[2 * n + t], d = q[3 * n + t], e = q[4 * n + t];
     out[t] = fast ? nyw::weno5<true>(a, b, c, d, e) : nyw::weno5<false>(a, b, c, d, e);
+}
+
+// fp64 pipe peak: eight independent DFMA chains per thread, no memory traffic
+__global__ void __launch_bounds__(512)
+k_fp64_peak(double* __restrict__ out, int iters, double seed)
+{
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 0.999999, c = 1e-9;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll 4
+        for (int u = 0; u < 4; u++) {
+            a0 = __fma_rn(a0, m, c); a1 = __fma_rn(a1, m, c); a2 = __fma_rn(a2, m, c); a3 = __fma_rn(a3, m, c);
+            a4 = __fma_rn(a4, m, c); a5 = __fma_rn(a5, m, c); a6 = __fma_rn(a6, m, c); a7 = __fma_rn(a7, m, c);
+        }
+    }
+    const double r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (r == 12345.678) out[0] = r;               // never true: keeps the chains alive
 }
 
 __global__ void __launch_bounds__(256)
@@ -315,6 +341,42 @@ static int launch_upwind(ny_ctx* ctx, const double* trac, const double* Ux, cons
     TrUpd upd;
     memset(&upd, 0, sizeof(upd));
     if (updp) upd = *updp;
+    Ext x = make_ext(e);
+    ny_prof_scope ps(ctx, NY_PROF_RHS_TRACER, st);
+    // k_up3 (ny_up3.cuh), the plane-marching TMA kernel that covers the whole array, is bit-identical to k_upwind2 but
+    // NOT faster: 4.07 ms against 4.05 ms per 512^3 launch (both end up at ~1965 MHz and 960-990 W, next to the board's
+    // 1 kW cap; profiles/r2_d_*).  It therefore only runs when asked for (ny_set_momentum_variant(ctx, 2)), which the
+    // parity tests do.
+    bool use3 = !diff && ctx->mom_variant == 2 && (e.nx & 1) == 0;
+    {
+        const void* ptrs[] = {trac, Ux, Uy, Uz};
+        for (const void* p : ptrs) use3 = use3 && (reinterpret_cast<uintptr_t>(p) & 15) == 0;
+    }
+    if (use3) {
+        using namespace u3;
+        Maps tm;
+        int r = ny_tma_encode_3d(&tm.t, trac, e.nx, e.ny, e.nz, PT, TY + 6, 1);
+        if (r == NY_OK) r = ny_tma_encode_3d(&tm.Ux, Ux, e.nx, e.ny, e.nz, PU, TY, 1);
+        if (r == NY_OK) r = ny_tma_encode_3d(&tm.Uy, Uy, e.nx, e.ny, e.nz, PU, TY + 1, 1);
+        if (r == NY_OK) r = ny_tma_encode_3d(&tm.Uz, Uz, e.nx, e.ny, e.nz, PU, TY, 1);
+        if (r != NY_OK) return r;
+        int kchunk = 32;                              // see the note on chunk length in launch_momentum
+        { const char* v = getenv("NY_UP3_KCHUNK"); if (v && atoi(v) > 0) kchunk = atoi(v); }
+        if (kchunk > e.nz) kchunk = e.nz;
+        dim3 grid((e.nx + TX - 1) / TX, (e.ny + TY - 1) / TY, (e.nz + kchunk - 1) / kchunk);
+        static bool attr_set[2] = {false, false};
+        const int fa = ctx->fast_arith ? 1 : 0;
+        if (!attr_set[fa]) {
+            cudaError_t ce = fa ? cudaFuncSetAttribute(k_up3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)
+                                : cudaFuncSetAttribute(k_up3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+            if (ce != cudaSuccess) { ny_set_error("k_up3: cannot reserve %d bytes of shared memory", SMEM); return NY_ERR_CUDA; }
+            attr_set[fa] = true;
+        }
+        if (fa) k_up3<true><<<grid, NW * 32, SMEM, st>>>(tm, trac, Uz, dtrac, x, kchunk, upd);
+        else k_up3<false><<<grid, NW * 32, SMEM, st>>>(tm, trac, Uz, dtrac, x, kchunk, upd);
+        NY_CHECK_LAUNCH(ctx);
+        return NY_OK;
+    }
     const int gx = (e.nx + 30) / 31, gy = (e.ny + UP_NW - 2) / (UP_NW - 1);
     // split k so that the launch has ~32 CTAs per SM; each chunk pays one extra plane of z fluxes
     long long want = ((long long)ctx->num_sms * 32 + (long long)gx * gy - 1) / ((long long)gx * gy);
@@ -322,8 +384,6 @@ static int launch_upwind(ny_ctx* ctx, const double* trac, const double* Ux, cons
     int kchunk = (e.nz + nchunk - 1) / nchunk;
     if (kchunk < 16) kchunk = e.nz < 16 ? e.nz : 16;
     dim3 grid(gx, gy, (e.nz + kchunk - 1) / kchunk);
-    Ext x = make_ext(e);
-    ny_prof_scope ps(ctx, NY_PROF_RHS_TRACER, st);
     if (ctx->fast_arith) {
         if (diff) k_upwind2<true, true><<<grid, UP_NW * 32, 0, st>>>(trac, Ux, Uy, Uz, dtrac, cx, cy, cz, x, kchunk, upd);
         else k_upwind2<true, false><<<grid, UP_NW * 32, 0, st>>>(trac, Ux, Uy, Uz, dtrac, cx, cy, cz, x, kchunk, upd);
@@ -345,17 +405,25 @@ static int launch_momentum(ny_ctx* ctx, const double* Ux, const double* Uy, cons
     memset(&upd, 0, sizeof(upd));
     if (updp) upd = *updp;
     ny_prof_scope ps(ctx, NY_PROF_RHS_MOMENTUM, st);
-    // one launch of the cell-parallel kernel over a box of cells, with a block shape that suits the box
-    auto launch_box = [&](CellBox cb, dim3 block) -> int {
-        if (cb.i0 >= cb.i1 || cb.j0 >= cb.j1 || cb.k0 >= cb.k1) return NY_OK;
-        dim3 grid((cb.i1 - cb.i0 + block.x - 1) / block.x, (cb.j1 - cb.j0 + block.y - 1) / block.y,
-                  (cb.k1 - cb.k0 + block.z - 1) / block.z);
+    // one launch of the cell-parallel kernel over a list of boxes, each with a block shape that suits it
+    CellBoxes boxes;
+    boxes.n = 0; boxes.total = 0;
+    auto add_box = [&](int i0, int i1, int j0, int j1, int k0, int k1, int bx, int by, int bz) {
+        if (i0 >= i1 || j0 >= j1 || k0 >= k1) return;
+        CellBox& cb = boxes.box[boxes.n++];
+        cb.i0 = i0; cb.i1 = i1; cb.j0 = j0; cb.j1 = j1; cb.k0 = k0; cb.k1 = k1; cb.bx = bx; cb.by = by; cb.bz = bz;
+        cb.gx = (i1 - i0 + bx - 1) / bx; cb.gy = (j1 - j0 + by - 1) / by;
+        cb.start = boxes.total;
+        boxes.total += cb.gx * cb.gy * ((k1 - k0 + bz - 1) / bz);
+    };
+    auto launch_boxes = [&]() -> int {
+        if (boxes.total == 0) return NY_OK;
         if (ctx->fast_arith && VORTEX)
-            k_momentum<true, ACCUM, VORTEX, BERN><<<grid, block, 0, st>>>(Ux, Uy, Uz, wx, wy, wz, ke, b, dux, duy, duz, cff,
-                                                                          with_b, make_ext(e), upd, cb);
+            k_momentum<true, ACCUM, VORTEX, BERN><<<boxes.total, 256, 0, st>>>(Ux, Uy, Uz, wx, wy, wz, ke, b, dux, duy, duz, cff,
+                                                                              with_b, make_ext(e), upd, boxes);
         else
-            k_momentum<false, ACCUM, VORTEX, BERN><<<grid, block, 0, st>>>(Ux, Uy, Uz, wx, wy, wz, ke, b, dux, duy, duz, cff,
-                                                                           with_b, make_ext(e), upd, cb);
+            k_momentum<false, ACCUM, VORTEX, BERN><<<boxes.total, 256, 0, st>>>(Ux, Uy, Uz, wx, wy, wz, ke, b, dux, duy, duz, cff,
+                                                                               with_b, make_ext(e), upd, boxes);
         NY_CHECK_LAUNCH(ctx);
         return NY_OK;
     };
@@ -371,7 +439,10 @@ static int launch_momentum(ny_ctx* ctx, const double* Ux, const double* Uy, cons
         const void* ptrs[] = {Ux, Uy, Uz, wx, wy, wz, ke, with_b ? b : ke};
         for (const void* p : ptrs) use3 = use3 && (reinterpret_cast<uintptr_t>(p) & 15) == 0;
     }
-    if (!use3) return launch_box({0, e.nx, 0, e.ny, 0, e.nz}, dim3(32, 4, 2));
+    if (!use3) {
+        add_box(0, e.nx, 0, e.ny, 0, e.nz, 32, 4, 2);
+        return launch_boxes();
+    }
     {
         using namespace m3;
         Maps tm;
@@ -405,15 +476,15 @@ static int launch_momentum(ny_ctx* ctx, const double* Ux, const double* Uy, cons
         else k_mom3<false><<<grid, TX * TY, SMEM, st>>>(tm, Uz, wx, wy, dux, duy, duz, cff, with_b, make_ext(e), kchunk, upd);
         NY_CHECK_LAUNCH(ctx);
     }
-    // the frame: two z slabs over the whole plane, two y slabs between them, two x slabs between those
+    // the frame in one launch: two z slabs over the whole plane, two y slabs between them, two x slabs between those
     const int x1 = e.nx - 3, y1 = e.ny - 3, z1 = e.nz - 3;
-    int r = launch_box({0, e.nx, 0, e.ny, 0, 3}, dim3(32, 8, 1));
-    if (r == NY_OK) r = launch_box({0, e.nx, 0, e.ny, z1, e.nz}, dim3(32, 8, 1));
-    if (r == NY_OK) r = launch_box({0, e.nx, 0, 3, 3, z1}, dim3(32, 1, 8));
-    if (r == NY_OK) r = launch_box({0, e.nx, y1, e.ny, 3, z1}, dim3(32, 1, 8));
-    if (r == NY_OK) r = launch_box({0, 3, 3, y1, 3, z1}, dim3(4, 8, 8));
-    if (r == NY_OK) r = launch_box({x1, e.nx, 3, y1, 3, z1}, dim3(4, 8, 8));
-    return r;
+    add_box(0, e.nx, 0, e.ny, 0, 3, 32, 8, 1);
+    add_box(0, e.nx, 0, e.ny, z1, e.nz, 32, 8, 1);
+    add_box(0, e.nx, 0, 3, 3, z1, 32, 1, 8);
+    add_box(0, e.nx, y1, e.ny, 3, z1, 32, 1, 8);
+    add_box(0, 3, 3, y1, 3, z1, 4, 8, 8);
+    add_box(x1, e.nx, 3, y1, 3, z1, 4, 8, 8);
+    return launch_boxes();
 }
 
 extern "C" int ny_set_arith(ny_ctx* ctx, int fast)
@@ -436,6 +507,40 @@ extern "C" int ny_debug_weno5(ny_ctx* ctx, const double* q, double* out, long lo
     NY_REQUIRE(ctx && q && out && n > 0, "bad argument");
     k_debug_weno5<<<(unsigned)((n + 255) / 256), 256, 0, ny_stream(stream)>>>(q, out, n, ctx->fast_arith);
     NY_CHECK_LAUNCH(ctx);
+    return NY_OK;
+}
+
+// Sustained rate of the fp64 pipe under this board's power cap: runs DFMA-only launches back to back for about
+// `seconds` and returns fp64 (warp-wide) instructions issued per second summed over the device, with the elapsed
+// time measured by CUDA events on `stream`.  The denominator of the WENO kernels' pipe fraction (bench.py).
+extern "C" int ny_debug_fp64_peak(ny_ctx* ctx, double seconds, double* dp_warp_instr_per_s, void* stream)
+{
+    NY_REQUIRE(ctx && dp_warp_instr_per_s && seconds > 0.0 && seconds <= 10.0, "bad argument");
+    cudaStream_t st = ny_stream(stream);
+    const int iters = 1 << 14, blocks = 4 * (ctx->num_sms > 0 ? ctx->num_sms : 148);
+    cudaEvent_t e0, e1;
+    NY_CUDA(cudaEventCreate(&e0));
+    NY_CUDA(cudaEventCreate(&e1));
+    k_fp64_peak<<<blocks, 512, 0, st>>>(ctx->d_scratch, iters, 1.0);           // warm-up, also times one launch
+    NY_CUDA(cudaEventRecord(e0, st));
+    k_fp64_peak<<<blocks, 512, 0, st>>>(ctx->d_scratch, iters, 1.0);
+    NY_CUDA(cudaEventRecord(e1, st));
+    NY_CUDA(cudaEventSynchronize(e1));
+    float ms1 = 0.f;
+    NY_CUDA(cudaEventElapsedTime(&ms1, e0, e1));
+    int n = (int)(seconds * 1e3 / (ms1 > 0.01f ? ms1 : 0.01f));
+    n = n < 1 ? 1 : (n > 2000 ? 2000 : n);
+    NY_CUDA(cudaEventRecord(e0, st));
+    for (int r = 0; r < n; r++) k_fp64_peak<<<blocks, 512, 0, st>>>(ctx->d_scratch, iters, 1.0);
+    NY_CUDA(cudaEventRecord(e1, st));
+    NY_CUDA(cudaEventSynchronize(e1));
+    NY_CHECK_LAUNCH(ctx);
+    float ms = 0.f;
+    NY_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    // per launch: blocks * 16 warps * iters * 32 DFMA
+    *dp_warp_instr_per_s = (double)n * blocks * 16.0 * iters * 32.0 / (ms * 1e-3);
     return NY_OK;
 }
 

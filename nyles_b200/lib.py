@@ -103,6 +103,7 @@ _PROTOS = {
     "ny_diag_post_max_speed2": ([_P, C.POINTER(_D), _P], _I),
     "ny_debug_weno5": ([_P, _P, _P, _LL, _P], _I),
     "ny_debug_weno3": ([_P, _P, _P, _LL, _P], _I),
+    "ny_debug_fp64_peak": ([_P, _D, C.POINTER(_D), _P], _I),
     "ny_debug_div": ([_P, _P, _P, _P, _LL, C.POINTER(_LL), _P], _I),
 }
 

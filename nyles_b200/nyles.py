@@ -145,10 +145,21 @@ class Nyles(object):
         the layout in which a caller of the reference's f2py/ctypes boundary holds its NumPy state."""
         return [torch.empty(t.shape, dtype=t.dtype, device="cpu", pin_memory=True) for t in self.prognostic_tensors()]
 
-    def step_host(self, t, host_state):
+    def step_host(self, t, host_state, modified=False):
         """One model step on HOST buffers: upload the prognostic state, compute dt, step, download the
         new state into the same buffers.  Returns dt.  This is the call whose cost bench.py reports as
         `e2e`: what a user pays who keeps the state in host memory, as the reference does.
+
+        modified=False (default): the caller promises that host_state still holds what the previous
+        step_host (or the copy from prognostic_tensors()) left there.  The diagnostic fields U, vor, ke, p,
+        the multigrid's warm start and the LFAM3 history on the device are then consistent with the upload
+        and the step costs what a step costs.
+        modified=True: the caller has edited the buffers (a restart, an assimilation step, a forcing applied on
+        the host).  The upload is followed by diagnose_var -- halo fills, projection, U, vorticity, kinetic
+        energy, from a zero first guess of the pressure -- exactly as Nyles.run() starts from a freshly written
+        state (core/nyles.py:125), the cached
+        max|U|^2 is dropped and the LFAM3 scheme restarts with its Euler start-up step
+        (core/timescheme.py:131-139), because its stored time levels no longer belong to this state.
         The projection that ends a step only changes u, so on a domain without halos the other fields
         (b, passive tracers) start their way back over PCIe on a second stream as soon as the time scheme
         has written them, underneath that projection."""
@@ -156,6 +167,14 @@ class Nyles(object):
         dev = self.prognostic_tensors()
         for h, d in zip(host_state, dev):
             d.copy_(h, non_blocking=True)
+        if modified:
+            self.model._umax_key = None
+            # a run that starts from this state has no previous pressure to warm-start from
+            mg = self.model.mg
+            mg.set_array(torch.zeros(mg.get_arrayshape(1), dtype=torch.float64, device=dev[0].device), ivar=1)
+            self.model.diagnose_var(self.model.state)
+            if hasattr(self.model.timescheme, "first"):
+                self.model.timescheme.first = True
         dt = self.compute_dt()
         names = self.model.state.get_prognostic_scalars()
         early = []

@@ -219,6 +219,66 @@ def test_views_survive_the_buffer_rotation_and_passive_tracers_follow():
     assert float(st.u["i"].tensor.abs().max()) > 0
 
 
+def test_step_host_honours_edited_host_buffers():
+    """step_host(modified=True): the caller has edited the host buffers, so the upload must be followed by
+    diagnose_var and an Euler start-up step, as a run that begins from that state does (core/nyles.py:125,
+    core/timescheme.py:131-139).  Checked against the oracle restarted from the same edited state."""
+    kw = dict(nx=32, ny=16, nz=16, geometry="closed", Lx=4.0, Ly=2.0, Lz=2.0, cfl=0.8, dt_max=0.05)
+    ny = make_nyles(kw)
+    o = M.LES(M.make_param(**kw))
+    rng = np.random.default_rng(33)
+    ic = np.tanh((o.grid.x_b - 2.0 + 0.1 * rng.standard_normal(o.grid.x_b.shape)) / (2 * o.grid.dx))
+    ny.model.state.b.view("i")[:] = ic
+    ny.model.diagnose_var(ny.model.state)
+    t = 0.0
+    for n in range(3):
+        dt = ny.compute_dt()
+        ny.model.forward(t, dt)
+        t += dt
+    host = ny.allocate_host_state()
+    for h, d in zip(host, ny.prognostic_tensors()):
+        h.copy_(d)
+    # the edit: a warm blob dropped into b, a kick added to u_i (names in the order of get_prognostic_scalars)
+    names = ny.model.state.get_prognostic_scalars()
+    hb, hu = host[names.index("b")], host[names.index("u_i")]
+    hb[4:10, 4:10, 8:20] += 0.5
+    hu[:, :, 10:14] += 0.01
+    # the oracle starts a fresh run from the edited state
+    for name, h in zip(names, host):
+        o.state.get(name).view("i")[:] = h.numpy()
+    o.diagnose_var(o.state)
+    for n in range(3):
+        dt_o = o.compute_dt()
+        dt = ny.step_host(t, host, modified=(n == 0))
+        assert abs(dt - dt_o) <= 1e-12 * dt_o, "dt differs at step %d after the edit" % n
+        o.forward(t, dt_o)
+        t += dt_o
+    for name, h in zip(names, host):
+        assert relerr(h.numpy(), o.state.get(name).data) <= 1e-10, name
+
+
+def test_sub_views_follow_the_field_through_buffer_rotation():
+    """A sub-view kept across steps (bint = b.view('i')[k0:k1]) stays bound to the Scalar, not to the buffer the
+    field lived in when the view was taken (the fused step rotates buffers; NumPy views of the reference stay valid)."""
+    kw = dict(nx=32, ny=16, nz=16, geometry="closed", Lx=4.0, Ly=2.0, Lz=2.0, cfl=0.8, dt_max=0.05)
+    ny = make_nyles(kw)
+    rng = np.random.default_rng(34)
+    ny.model.state.b.view("i")[:] = np.tanh(rng.standard_normal((16, 16, 32)))
+    ny.model.diagnose_var(ny.model.state)
+    sub = ny.model.state.b.view("i")[2:5, :, 3:9]
+    subj = ny.model.state.b.view("j")[3:9][:, 2:5]
+    t = 0.0
+    for n in range(3):
+        dt = ny.compute_dt()
+        ny.model.forward(t, dt)
+        t += dt
+        full = ny.model.state.b.tensor.cpu().numpy()
+        assert np.array_equal(np.asarray(sub), full[2:5, :, 3:9])
+        assert np.array_equal(np.asarray(subj), full.transpose(2, 0, 1)[3:9][:, 2:5])
+    sub[:] = 7.0                                   # writes land in the live field
+    assert float(ny.model.state.b.tensor[2:5, :, 3:9].min()) == 7.0
+
+
 def test_vortex_force_work_diagnostic():
     """core/online_diag.py VFwork after a few steps of a developing flow: the work field equals the oracle's
     bit for bit (same elementwise order), its interior sum to round-off."""

@@ -108,6 +108,18 @@ def main():
             print("rhs %-9s fast=%d mom=%d n=%d: tracer %.3f ms (%.0f GB/s alg), momentum %.3f ms (%.0f GB/s alg)"
                   % (label, a.fast, a.mom, n, t_tr, 40 * cells / t_tr / 1e6, t_rhs - t_tr, 88 * cells / (t_rhs - t_tr) / 1e6), flush=True)
             if a.sustained:
+                t, c = sustained(lambda: lib.check(L.ny_rhs(ctx, lib.ptr(b), lib.ptr(Ux), lib.ptr(Uy), lib.ptr(Uz), lib.ptr(wx), lib.ptr(wy),
+                                                            lib.ptr(wz), lib.ptr(ke), lib.ptr(out[0]), lib.ptr(out[1]), lib.ptr(out[2]),
+                                                            lib.ptr(out[3]), 0.25, 1, e, st)))
+                print("   sustained momentum alone (Euler flag: no tracer launch) %.3f ms, %s" % (t, c), flush=True)
+                lib.prof_start()
+                for _ in range(5):
+                    lib.check(L.ny_rhs(ctx, lib.ptr(b), lib.ptr(Ux), lib.ptr(Uy), lib.ptr(Uz), lib.ptr(wx), lib.ptr(wy),
+                                       lib.ptr(wz), lib.ptr(ke), lib.ptr(out[0]), lib.ptr(out[1]), lib.ptr(out[2]),
+                                       lib.ptr(out[3]), 0.25, 0, e, st))
+                prof = lib.prof_collect()
+                lib.prof_start(0)
+                print("   event-timed families: " + ", ".join("%s %.3f ms" % (k, v[0] / 5) for k, v in prof.items() if v[1]), flush=True)
                 t, c = sustained(lambda: lib.check(L.ny_upwind(ctx, lib.ptr(b), lib.ptr(Ux), lib.ptr(Uy), lib.ptr(Uz), lib.ptr(out[0]), e, st)))
                 print("   sustained tracer %.3f ms, %s" % (t, c), flush=True)
                 t, c = sustained(lambda: lib.check(L.ny_vortex_force(ctx, lib.ptr(Ux), lib.ptr(Uy), lib.ptr(Uz), lib.ptr(wx), lib.ptr(wy),
