@@ -72,6 +72,7 @@ enum { NY_PROF_RHS_TRACER = 0, NY_PROF_RHS_MOMENTUM, NY_PROF_VORT_KE, NY_PROF_DI
        NY_PROF_MG_PROLONG_FINE, NY_PROF_MG_NORM, NY_PROF_MG_COARSE, NY_PROF_MG_EMBED,
        NY_PROF_MG_DOWN_FINE,   /* fused smooth + residual + restriction of level 1 */
        NY_PROF_MG_UP_FINE,     /* fused prolongation + smooth (+ residual norm) of level 1 */
+       NY_PROF_GRADP_POST,     /* u -= grad p fused with U, vorticity, kinetic energy (ny_mg_project_post) */
        NY_PROF_NTAGS };
 
 /* ---- context ---------------------------------------------------------------------- */
@@ -98,12 +99,11 @@ const char* ny_prof_name(int tag);
  * Differences are a few ulp, far inside the 1e-12 parity bar (tests/test_gpu_operators.py). */
 int  ny_set_arith(ny_ctx* ctx, int fast);
 int  ny_get_arith(ny_ctx* ctx);
-/* Which kernels evaluate the WENO right-hand sides.  0 (default): the momentum equations run the plane-marching
- * TMA kernel (k_mom3) on the cells whose six sweeps are interior (3 <= s <= n-4 on every axis) for grids of at least
- * 2^18 cells and the cell-parallel kernel on the 3-cell frame and on small grids; the tracer runs the cell-parallel
- * kernel.  1 = cell-parallel kernels only.  2 = the plane-marching TMA kernels (k_mom3, k_up3) wherever they are
- * legal (even nx, 16-byte aligned arrays), whatever the size.  All variants are bit-identical; the switch exists for
- * tests and timing. */
+/* Which kernel evaluates the fused momentum right-hand side on the cells whose six WENO sweeps are interior
+ * (3 <= s <= n-4 on every axis): 0 (default) = the plane-marching TMA kernel (k_mom3) for grids of at least 2^18
+ * cells, the cell-parallel kernel below that; 1 = always the cell-parallel kernel; 2 = the TMA kernel wherever it
+ * is legal (even nx, 16-byte aligned arrays).  The 3-cell frame around those cells always runs the cell-parallel
+ * kernel.  All variants are bit-identical; the switch exists for tests and timing. */
 int  ny_set_momentum_variant(ny_ctx* ctx, int variant);
 
 /* ---- f2py kernel replacements ------------------------------------------------------ */
@@ -245,7 +245,9 @@ int  ny_mg_create(ny_ctx*, int nx, int ny, int nz, int topology, ny_mg** out);
  * (z halos filled from the neighbours through NCCL); small levels are gathered and solved
  * redundantly (mg_setup.f90:275-293).  Collective: every rank must make the same calls. */
 int  ny_mg_create_slab(ny_ctx*, ny_comm* comm, int nx, int ny, int nz_global, int topology, ny_mg** out);
-/* slab multigrids created afterwards gather every level with at most `cells` global cells
+/* Tuning defaults.  The four setters below change process-wide DEFAULTS that a multigrid copies when it is created
+ * (ny_mg_create / ny_mg_create_slab); an existing multigrid keeps the values it was born with.
+ * slab multigrids created afterwards gather every level with at most `cells` global cells
  * (default 64^3); a level whose slab is thinner than 4 planes is gathered in any case */
 void ny_mg_set_gather_cells(long long cells);
 /* slab levels with at least `cells` local cells compute the planes next to their slab neighbours first and
@@ -297,7 +299,26 @@ int  ny_mg_solve_directly(ny_mg*, double* p, const double* div, ny_ext e, const 
 int  ny_mg_project(ny_mg*, double* ux, double* uy, double* uz, double* div, double* p,
                    double idx2, double idy2, double idz2, ny_ext e, const int lo[3], double scale,
                    ny_mg_stats* stats_host, void* stream);
+/* ny_mg_project followed by ny_diag_post with the two passes over u merged (15 arrays through HBM instead of 18):
+ * the projected velocity is written to uo[] (must not alias u[]), which the caller then uses as u.  Only for domains
+ * whose u needs no halo refresh between the projection and the diagnostics (closed box, one rank). */
+int  ny_mg_project_post(ny_mg*, const double* ux, const double* uy, const double* uz,
+                        double* uxo, double* uyo, double* uzo, double* div, double* p,
+                        double* Ux, double* Uy, double* Uz, double* wx, double* wy, double* wz, double* ke,
+                        double idx2, double idy2, double idz2, double fparam, ny_ext e, const int lo[3],
+                        double scale, ny_mg_stats* stats_host, void* stream);
 int  ny_mg_op(ny_mg*, int op, int lev, void* stream);
+
+/* ---- the linear (non-WENO) upwind branch ---------------------------------------------------------
+ * What fortran_upwind.upwind and fortran_vortex_force.vortex_force_direc / _flip compute when their local flag
+ * `linear` is .true. (core/fortran_upwind.f90:33-64, core/fortran_vortex_force.f90:39-64,118-143, with
+ * core/interpolate_tracer.f90 / core/interpolate.f90; orders 1..5, REAL(4) coefficients).  The reference ships with
+ * linear = .false., so these are never reached there; nyles_b200.LINEAR_UPWIND switches the models onto them. */
+int  ny_upwind_linear(ny_ctx*, const double* trac, const double* Ux, const double* Uy, const double* Uz,
+                      double* dtrac, int order, ny_ext e, void* stream);
+int  ny_vortex_force_linear(ny_ctx*, const double* Ux, const double* Uy, const double* Uz,
+                            const double* wx, const double* wy, const double* wz,
+                            double* dux, double* duy, double* duz, int order, ny_ext e, void* stream);
 
 /* ---- arithmetic primitives, exposed for the parity tests -------------------------------------
  * ny_debug_weno5: out[t] = weno5(q0[t], q1[t], q2[t], q3[t], q4[t]) (core/weno.f90:25-54) in the

@@ -14,3 +14,10 @@ __version__ = "0.1.0"
 # True  = re-associated smooth part of weno5 (one reciprocal, FMAs; beta/tau5 still exact): every
 #         single RHS stays within 1e-12 of the reference arithmetic and the kernels run ~1.5x faster.
 FAST_ARITH = False
+
+# The reference's Fortran carries a second, linear (non-WENO) upwind branch behind a local flag `linear` that is
+# .false. as shipped (core/fortran_upwind.f90:31, core/fortran_vortex_force.f90:28,108), so orderA / orderVF are
+# ignored at run time there.  True = models built afterwards evaluate the tracer advection and the vortex force with
+# that branch (core/interpolate_tracer.f90, core/interpolate.f90) at the orders orderA / orderVF -- what the reference
+# does after editing the flag.  The per-operator launches are used (no fused RHS + time-scheme launches).
+LINEAR_UPWIND = False

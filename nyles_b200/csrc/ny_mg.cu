@@ -79,6 +79,9 @@ struct ny_mg {
     int xper, yper, zper;
     int box;                               // default mask: analytic coefficients are valid
     int glev;                              // first gathered level (0-based); 0 on one rank
+    // tuning, fixed when the multigrid is created (copied from the process-wide defaults that the ny_mg_set_* calls
+    // and the NY_MG_* environment variables set; a setter never changes an existing multigrid)
+    long long tail_cells, split_tiles_min, overlap_cells;
     int below, above;                      // slab neighbours (-1: none)
     double tol, omega;
     Level lev[MAXLEV];
@@ -754,15 +757,99 @@ __device__ __forceinline__ double tail_resid(const double* x, const double* b, c
     return b[c] + diag * x[c] - s;
 }
 
+constexpr int TAIL_STAGE = 2048;          // doubles of staging for array sections that overlap themselves
+
+// array section dst = src with Fortran semantics (right-hand side evaluated first), Fortran indices as in
+// k_box_copy; every thread of the CTA takes part, the section is complete when the call returns
+__device__ __forceinline__ void tail_assign_box(double* a, const Box& g, int di0, int dj0, int dk0, int si0, int sj0, int sk0,
+                                                int ni, int nj, int nk, bool staged, double* stage)
+{
+    const int total = ni * nj * nk;
+    auto at = [&](int i, int j, int k) { return (long long)(k - 1) * g.sk + (long long)(j - 1 + NH) * g.sj + (i - 1 + NH); };
+    if (total <= 0) return;
+    if (staged) {
+        for (int t = threadIdx.x; t < total; t += TAIL_THREADS) {
+            const int i = t % ni, q = t / ni, j = q % nj, k = q / nj;
+            stage[t] = a[at(si0 + i, sj0 + j, sk0 + k)];
+        }
+        __syncthreads();
+        for (int t = threadIdx.x; t < total; t += TAIL_THREADS) {
+            const int i = t % ni, q = t / ni, j = q % nj, k = q / nj;
+            a[at(di0 + i, dj0 + j, dk0 + k)] = stage[t];
+        }
+    } else {
+        for (int t = threadIdx.x; t < total; t += TAIL_THREADS) {
+            const int i = t % ni, q = t / ni, j = q % nj, k = q / nj;
+            a[at(di0 + i, dj0 + j, dk0 + k)] = a[at(si0 + i, sj0 + j, sk0 + k)];
+        }
+    }
+    __syncthreads();
+}
+
+// periodic halo fill of a replicated level inside the tail: the rule of k_fill_periodic where every wrapped axis is
+// at least nh wide, the statement sequence of mod_halo.f90:235-262 (fill_sequential) on the tiny levels below that
+__device__ __forceinline__ void tail_fill(double* a, const Box& g, double* stage)
+{
+    const bool wz = g.zlo && g.zhi;
+    if (!(g.xper || g.yper || wz)) return;
+    const int nx = g.nx, ny = g.ny, nz = g.nz, nzi = nz - 2 * NH;
+    const bool simple = (!g.xper || nx >= NH) && (!g.yper || ny >= NH) && (!wz || nzi >= NH);
+    if (simple) {
+        const int tx = nx + 2 * NH, ty = ny + 2 * NH, n = tx * ty * nz;
+        for (int t = threadIdx.x; t < n; t += TAIL_THREADS) {
+            const int ai = t % tx, q = t / tx, aj = q % ty, ak = q / ty;
+            const bool hx = ai < NH || ai >= nx + NH, hy = aj < NH || aj >= ny + NH, hz = ak < NH || ak >= nz - NH;
+            int si = ai, sjj = aj, skk = ak;
+            if (hz && wz) skk = ak < NH ? ak + nzi : ak - nzi;
+            if (hx && hy) {
+                if (g.xper && g.yper) { si = ai < NH ? ai + nx : ai - nx; sjj = aj < NH ? aj + ny : aj - ny; }
+            } else if (hx) {
+                if (g.xper) si = ai < NH ? ai + nx : ai - nx;
+            } else if (hy) {
+                if (g.yper) sjj = aj < NH ? aj + ny : aj - ny;
+            }
+            if (si != ai || sjj != aj || skk != ak)
+                a[(long long)ak * g.sk + (long long)aj * g.sj + ai] = a[(long long)skk * g.sk + (long long)sjj * g.sj + si];
+        }
+        __syncthreads();
+        return;
+    }
+    const int nh = NH;
+    if (g.xper) {
+        const bool ov = nx < nh;
+        tail_assign_box(a, g, nx + 1, 1, 1, 1, 1, 1, nh, ny, nz, ov, stage);
+        tail_assign_box(a, g, 1 - nh, 1, 1, nx - nh + 1, 1, 1, nh, ny, nz, ov, stage);
+    }
+    if (g.yper) {
+        const bool ov = ny < nh;
+        tail_assign_box(a, g, 1, ny + 1, 1, 1, 1, 1, nx, nh, nz, ov, stage);
+        tail_assign_box(a, g, 1, 1 - nh, 1, 1, ny - nh + 1, 1, nx, nh, nz, ov, stage);
+    }
+    if (g.xper && g.yper) {
+        const bool ov = nx < nh || ny < nh;
+        tail_assign_box(a, g, nx + 1, ny + 1, 1, 1, 1, 1, nh, nh, nz, ov, stage);
+        tail_assign_box(a, g, 1 - nh, ny + 1, 1, nx - nh + 1, 1, 1, nh, nh, nz, ov, stage);
+        tail_assign_box(a, g, nx + 1, 1 - nh, 1, 1, ny - nh + 1, 1, nh, nh, nz, ov, stage);
+        tail_assign_box(a, g, 1 - nh, 1 - nh, 1, nx - nh + 1, ny - nh + 1, 1, nh, nh, nz, ov, stage);
+    }
+    if (wz) {
+        const bool ov = nzi < nh;
+        tail_assign_box(a, g, 1 - nh, 1 - nh, 1, 1 - nh, 1 - nh, nzi + 1, nx + 2 * nh, ny + 2 * nh, nh, ov, stage);
+        tail_assign_box(a, g, 1 - nh, 1 - nh, nz - nh + 1, 1 - nh, 1 - nh, nh + 1, nx + 2 * nh, ny + 2 * nh, nh, ov, stage);
+    }
+}
+
 __global__ void __launch_bounds__(TAIL_THREADS, 1)
 k_vcycle_tail(TailArgs a)
 {
+    __shared__ double stage[TAIL_STAGE];
     const double omega = a.omega, cff1 = a.cff1;
     auto smooth = [&](const TailLevel& L) {
         tail_sweep(L.x, L.y, L.b, L.g, omega, cff1, 1);
         __syncthreads();
         tail_sweep(L.y, L.x, L.b, L.g, omega, cff1, 0);
         __syncthreads();
+        tail_fill(L.x, L.g, stage);                      // operators.f90:168
     };
     for (int l = 0; l + 1 < a.n; l++) {                 // solvers.f90:41-46
         const TailLevel& F = a.lev[l];
@@ -786,6 +873,7 @@ k_vcycle_tail(TailArgs a)
         const long long nc = gc.sk * gc.nz;
         for (long long t = threadIdx.x; t < nc; t += TAIL_THREADS) C.x[t] = 0.0;   // operators.f90:209
         __syncthreads();
+        tail_fill(C.b, gc, stage);                       // operators.f90:211
     }
     smooth(a.lev[a.n - 1]);
     for (int l = a.n - 2; l >= 0; l--) {                // solvers.f90:51-54
@@ -808,6 +896,7 @@ k_vcycle_tail(TailArgs a)
             F.x[f] = F.x[f] + cf * (3 * pb + po);
         }
         __syncthreads();
+        tail_fill(F.x, g, stage);                        // operators.f90:242
         smooth(F);
     }
     // the fused legs of the finer levels rely on y == x on the wall halos of every level
@@ -1251,7 +1340,7 @@ int launch_leg(ny_mg* mg, cudaStream_t st, int lev, const Level& V, bool* exchan
     const long long n_inner = (long long)inner.nbx * inner.nby, n_frame = (long long)tgx * tgy - n_inner;
     auto launch = [&](int kz0, int kz1, cudaStream_t s) -> int {
         // (two launches only pay where each fills the machine several times: the large levels)
-        if (n_inner > 0 && mg->split_tiles && n_inner + n_frame >= g_split_tiles) {
+        if (n_inner > 0 && mg->split_tiles && n_inner + n_frame >= mg->split_tiles_min) {
             LegGeom q = leg_geom(mg, F, kz1 - kz0, LY::tj, extra, POST == POST_RESTRICT, n_inner);
             LegGeom qf = leg_geom(mg, F, kz1 - kz0, LY::tj, extra, POST == POST_RESTRICT, n_frame > 0 ? n_frame : 1);
             if (POST == POST_NORM && nparts + q.nparts + qf.nparts > MAX_PARTIALS) { ny_set_error("too many partial sums"); return NY_ERR_ARG; }
@@ -1285,7 +1374,7 @@ int launch_leg(ny_mg* mg, cudaStream_t st, int lev, const Level& V, bool* exchan
     // worth it only where the interior part runs much longer than the exchange (measured: level 1 of a 512^3
     // slab yes, its 256^3-per-8 coarser levels no)
     // (and the faces are large: 1024^2 planes gain 3 ms per step at 8 GPUs, 512^2 planes lose 0.5 ms at 2)
-    const bool big = (long long)F.nx * F.ny * nzi >= g_overlap_cells && (long long)F.nx * F.ny * 32 >= g_overlap_cells;
+    const bool big = (long long)F.nx * F.ny * nzi >= mg->overlap_cells && (long long)F.nx * F.ny * 32 >= mg->overlap_cells;
     if (mg->comm && !F.gathered && (lo || hi) && !mg->xper && !mg->yper && coarse_dist && nzi >= 4 * LEG_EDGE && big) {
         ny_comm* cm = mg->comm;
         if (lo) TRY(launch(0, LEG_EDGE, st));
@@ -1359,15 +1448,21 @@ int up_leg(ny_mg* mg, cudaStream_t st, int lev, bool with_norm, int* nparts)
 }
 
 // first level (1-based) of the V-cycle tail that k_vcycle_tail runs, or nlevels + 1 when there is none:
-// closed box on analytic coefficients, levels replicated on every rank, at most g_tail_cells cells each
+// box on analytic coefficients (closed or periodic), levels replicated on every rank, at most tail_cells cells each
 int tail_first(const ny_mg* mg)
 {
     const int none = mg->nlevels + 1;
-    if (!mg->box || !mg->fused || !mg->tail || mg->xper || mg->yper || mg->zper) return none;
+    if (!mg->box || !mg->fused || !mg->tail) return none;
     int lt = mg->nlevels;
     while (lt >= 1) {
         const Level& L = mg->lev[lt - 1];
-        if (!L.gathered || L.zlo || L.zhi || (long long)L.nx * L.ny * (L.nz - 2 * NH) > g_tail_cells) break;
+        // replicated levels only (their z ends are walls or a local periodic wrap, never a slab neighbour)
+        if (!L.gathered || L.zlo != mg->zper || L.zhi != mg->zper) break;
+        if ((long long)L.nx * L.ny * (L.nz - 2 * NH) > mg->tail_cells) break;
+        // tiny periodic levels stage their self-overlapping halo sections through shared memory
+        const bool wz = mg->zper;
+        const bool simple = (!mg->xper || L.nx >= NH) && (!mg->yper || L.ny >= NH) && (!wz || L.nz - 2 * NH >= NH);
+        if (!simple && L.n > (size_t)TAIL_STAGE) break;
         lt--;
     }
     lt++;
@@ -1495,15 +1590,18 @@ int create(ny_ctx* ctx, ny_comm* comm, int nx, int ny, int nz_global, int topolo
     NY_REQUIRE(topology >= NY_TOPO_CLOSED && topology <= NY_TOPO_XYZPERIO, "unknown topology");
     const int P = comm ? comm->nranks : 1, rank = comm ? comm->rank : 0;
     NY_REQUIRE(nz_global % P == 0, "global nz must be a multiple of the number of slabs");
-    {   // experiment switches (bench runs under torchrun): NY_MG_OVERLAP_CELLS, NY_MG_TAIL_CELLS
+    {   // experiment switches (bench runs under torchrun): NY_MG_OVERLAP_CELLS, NY_MG_TAIL_CELLS, NY_MG_GATHER_CELLS
         const char* e = getenv("NY_MG_OVERLAP_CELLS");
         if (e && *e) g_overlap_cells = atoll(e);
         e = getenv("NY_MG_TAIL_CELLS");
         if (e && *e) g_tail_cells = atoll(e);
+        e = getenv("NY_MG_GATHER_CELLS");
+        if (e && *e) g_gather_cells = atoll(e);
     }
     ny_mg* mg = new ny_mg();
     memset(mg, 0, sizeof(ny_mg));
     mg->ctx = ctx; mg->comm = P > 1 ? comm : nullptr; mg->nranks = P; mg->rank = rank;
+    mg->tail_cells = g_tail_cells; mg->split_tiles_min = g_split_tiles; mg->overlap_cells = g_overlap_cells;
     mg->nh = NH; mg->maxite = 20; mg->tol = 1e-6; mg->omega = 0.9;          // mg_types.f90:15-26
     mg->topology = topology;
     mg->xper = topology == NY_TOPO_XPERIO || topology == NY_TOPO_XYPERIO || topology == NY_TOPO_XYZPERIO;
@@ -1842,6 +1940,43 @@ extern "C" int ny_mg_project(ny_mg* mg, double* ux, double* uy, double* uz, doub
     k_extract_gradp<<<g.grid, g.block, 0, st>>>(mg->lev[0].x, p, ux, uy, uz, L, e.nz, e.ny, e.nx, lo[0], lo[1], lo[2], scale);
     LAUNCH_OK(mg);
     return NY_OK;
+}
+
+// diagnose_var's projection AND its diagnostics (core/model_les.py:108-123) around the solve: div from u, solve,
+// then ONE pass that writes p, the projected velocity (into uo: a cell's neighbours still read u), U, the vorticity,
+// the kinetic energy and max|U|^2 (ny_diag_post_max_speed2 reads it).  For domains without halos to refresh between
+// the two halves (closed box on one rank): the caller swaps u and uo afterwards.
+extern "C" int ny_mg_project_post(ny_mg* mg, const double* ux, const double* uy, const double* uz,
+                                  double* uxo, double* uyo, double* uzo, double* div, double* p,
+                                  double* Ux, double* Uy, double* Uz, double* wx, double* wy, double* wz, double* ke,
+                                  double idx2, double idy2, double idz2, double fparam, ny_ext e, const int lo[3],
+                                  double scale, ny_mg_stats* stats, void* stream)
+{
+    NY_REQUIRE(mg && ux && uy && uz && uxo && uyo && uzo && div && p && Ux && Uy && Uz && wx && wy && wz && ke && lo,
+               "null argument");
+    NY_REQUIRE(uxo != ux && uyo != uy && uzo != uz, "the projected velocity needs its own arrays");
+    Level& L = mg->lev[0];
+    const int nh = mg->nh;
+    NY_REQUIRE(lo[0] + e.nz <= L.nz && lo[1] + e.ny <= L.ny + 2 * nh && lo[2] + e.nx <= L.nx + 2 * nh &&
+               lo[0] >= 0 && lo[1] >= 0 && lo[2] >= 0, "model array does not fit the multigrid array");
+    // the fused pass reads x one cell beyond the model array on the + sides only where a gradient is taken
+    // (i < nx-1 etc.), i.e. never outside it
+    cudaStream_t st = ny_stream(stream);
+    ny_grid3 g = ny_cells_launch(e.nz, e.ny, e.nx);
+    {
+        ny_prof_scope ps(mg->ctx, NY_PROF_DIV, st);
+        k_div_embed<<<g.grid, g.block, 0, st>>>(ux, uy, uz, div, L.b, idx2, idy2, idz2, L, e.nz, e.ny, e.nx, lo[0], lo[1], lo[2]);
+        LAUNCH_OK(mg);
+    }
+    {
+        ny_prof_scope ps(mg->ctx, NY_PROF_HALO, st);
+        TRY(fill(mg, st, L, L.b));
+    }
+    mg->halo_ok = 1;
+    TRY(ny_mg_solve(mg, stats, stream));
+    const long long m0 = (long long)lo[0] * L.sk + (long long)lo[1] * L.sj + lo[2];
+    return ny_launch_gradp_post(mg->ctx, mg->lev[0].x, L.sj, L.sk, m0, scale, ux, uy, uz, p, uxo, uyo, uzo, Ux, Uy, Uz,
+                                wx, wy, wz, ke, idx2, idy2, idz2, fparam, e, st);
 }
 
 extern "C" int ny_mg_op(ny_mg* mg, int op, int lev, void* stream)

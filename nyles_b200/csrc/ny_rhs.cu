@@ -266,7 +266,158 @@ k_momentum(const double* __restrict__ Ux, const double* __restrict__ Uy, const d
 }
 
 #include "ny_mom3.cuh"
-#include "ny_up3.cuh"
+
+// ================================================================================================
+//  The linear (non-WENO) upwind branch of the reference: `linear = .true.` in fortran_upwind.f90:31 and
+//  fortran_vortex_force.f90:28,108 (a local flag, .false. as shipped, so dormant there), with the interpolations
+//  of core/interpolate_tracer.f90 / core/interpolate.f90, orders 1..5.  One thread per cell, every value the
+//  cell needs recomputed from its line neighbours; coefficients are the REAL(4) constant expressions promoted to
+//  double.  Not a hot path: written for parity, not for speed.
+// ================================================================================================
+namespace lin {
+constexpr double C1 = (double)(-(1.0f / 6.0f)), C2 = (double)(5.0f / 6.0f), C3 = (double)(2.0f / 6.0f);
+constexpr double E1 = (double)(-(1.0f / 12.0f)), E2 = (double)(7.0f / 12.0f);
+constexpr double B1 = (double)(2.0f / 60.0f), B2 = (double)(-(13.0f / 60.0f)), B3 = (double)(47.0f / 60.0f),
+                 B4 = (double)(27.0f / 60.0f), B5 = (double)(-(3.0f / 60.0f));
+
+// v(i): value at 1-based line position i.  P = qp flavour (coefficients c1 c2 c3 / b1..b5), M = mirrored.
+template <class V> __device__ __forceinline__ double third(bool plus, V v, int i)
+{
+    return plus ? C1 * v(i - 1) + C2 * v(i) + C3 * v(i + 1) : C3 * v(i - 1) + C2 * v(i) + C1 * v(i + 1);
+}
+template <class V> __device__ __forceinline__ double fifth(bool plus, V v, int i)
+{
+    return plus ? B1 * v(i - 2) + B2 * v(i - 1) + B3 * v(i) + B4 * v(i + 1) + B5 * v(i + 2)
+                : B5 * v(i - 2) + B4 * v(i - 1) + B3 * v(i) + B2 * v(i + 1) + B1 * v(i + 2);
+}
+
+// interpolate_tracer.f90:45-110: qp(i) (plus) or qm(i) at 1 <= i <= n for the odd orders, the centred qp(i)
+// (1 <= i <= n-1) for the even ones
+template <class V> __device__ __forceinline__ double interp_tr(int order, int n, bool plus, V v, int i)
+{
+    if (order == 5) {
+        if (i == 1 || i == n) return v(i);
+        if (i == 2 || i == n - 1) return third(plus, v, i);
+        return fifth(plus, v, i);
+    }
+    if (order == 3) return (i == 1 || i == n) ? v(i) : third(plus, v, i);
+    if (order == 1) return v(i);
+    if (order == 2) return 0.5 * (v(i) + v(i + 1));
+    /* order 4 */
+    if (i == 1) return E2 * (v(i) + v(i + 1)) + E1 * (v(i + 2));
+    if (i == n - 1) return E2 * (v(i) + v(i + 1)) + E1 * (v(i - 1));
+    return E2 * (v(i) + v(i + 1)) + E1 * (v(i - 1) + v(i + 2));
+}
+
+// interpolate.f90:34-110 (the flavour of the vortex force): qp(i) for 0 <= i <= n-1 (plus) or qm(i) for 1 <= i <= n
+// for the odd orders, qm(i) (1 <= i <= n) for the even ones.  Later assignments of the Fortran win.
+template <class V> __device__ __forceinline__ double interp_vf(int order, int n, bool plus, V v, int i)
+{
+    if (order == 5) {
+        if (i == 0) return 0.0;
+        if (i == n || i == n - 1 || i == 1) return v(i);
+        if (i == n - 2 || i == 2) return third(plus, v, i);
+        return fifth(plus, v, i);
+    }
+    if (order == 3) {
+        if (i == 0) return 0.0;
+        if (i == n || i == n - 1 || i == 1) return v(i);
+        return third(plus, v, i);
+    }
+    if (order == 1) return i == 0 ? 0.0 : v(i);
+    if (order == 2) return i == 1 ? 0.5 * v(1) : 0.5 * (v(i - 1) + v(i));
+    /* order 4 */
+    if (i == 1) return E2 * (v(i)) + E1 * (v(i + 1));
+    if (i == 2) return E2 * (v(i - 1) + v(i)) + E1 * (v(i + 1));
+    if (i == n) return E2 * (v(i - 1) + v(i)) + E1 * (v(i - 2));
+    return E2 * (v(i - 1) + v(i)) + E1 * (v(i - 2) + v(i + 1));
+}
+
+// flux through the face between line cells s and s+1 (0-based s), fortran_upwind.f90:43-63; the last face is closed
+template <class Q, class U> __device__ __forceinline__ double tracer_flux(int order, int n, int s, Q q, U u)
+{
+    if (s < 0 || s >= n - 1) return 0.0;
+    const int i = s + 1;                                  // Fortran position
+    auto v = [&](int p) { return q(p - 1); };
+    const double ui = u(s);
+    if ((order & 1) == 0) return ui * interp_tr(order, n, true, v, i);
+    const double UU = fabs(ui), up = 0.5 * (ui + UU), um = 0.5 * (ui - UU);
+    return up * interp_tr(order, n, true, v, i) + um * interp_tr(order, n, false, v, i + 1);
+}
+}  // namespace lin
+
+__global__ void __launch_bounds__(256)
+k_upwind_linear(const double* __restrict__ trac, const double* __restrict__ Ux, const double* __restrict__ Uy,
+                const double* __restrict__ Uz, double* __restrict__ dtrac, int order, Ext e)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int j = blockIdx.y * blockDim.y + threadIdx.y;
+    int k = blockIdx.z * blockDim.z + threadIdx.z;
+    if (i >= e.nx || j >= e.ny || k >= e.nz) return;
+    const long long c = (long long)k * e.sk + (long long)j * e.sj + i;
+    double acc = 0.0;                                     // tracer.py:70-71
+    {
+        auto q = [&](int p) { return trac[c + (p - i)]; };
+        auto u = [&](int p) { return Ux[c + (p - i)]; };
+        acc = acc + lin::tracer_flux(order, e.nx, i - 1, q, u) - lin::tracer_flux(order, e.nx, i, q, u);
+    }
+    {
+        auto q = [&](int p) { return trac[c + (long long)(p - j) * e.sj]; };
+        auto u = [&](int p) { return Uy[c + (long long)(p - j) * e.sj]; };
+        acc = acc + lin::tracer_flux(order, e.ny, j - 1, q, u) - lin::tracer_flux(order, e.ny, j, q, u);
+    }
+    {
+        auto q = [&](int p) { return trac[c + (long long)(p - k) * e.sk]; };
+        auto u = [&](int p) { return Uz[c + (long long)(p - k) * e.sk]; };
+        acc = acc + lin::tracer_flux(order, e.nz, k - 1, q, u) - lin::tracer_flux(order, e.nz, k, q, u);
+    }
+    dtrac[c] = acc;
+}
+
+// one sweep of the linear vortex force for the cell at 0-based line position s: res is updated in place with the
+// statements of fortran_vortex_force.f90:52-63 (direc, sign = -1) or :131-142 (flip, sign = +1)
+__device__ __forceinline__ double vf_linear(double res, int order, int sign, const double* __restrict__ US,
+                                            const double* __restrict__ W, long long cs, long long stride, long long tstride,
+                                            int s, int n)
+{
+    auto v = [&](int p) { return W[cs + (long long)(p - 1 - s) * stride]; };       // vU(p) = vort at line position p
+    if ((order & 1) == 0) {
+        const double qm = lin::interp_vf(order, n, false, v, s + 1);
+        return sign < 0 ? res - qm : res + qm;
+    }
+    const double s1 = 0.5 * (US[cs] + US[cs + tstride]);
+    const double s0 = s > 0 ? 0.5 * (US[cs - stride] + US[cs - stride + tstride]) : 0.0;
+    const double Ui = 0.5 * (s0 + s1), UU = fabs(Ui), up = 0.5 * (Ui + UU), um = 0.5 * (Ui - UU);
+    const double qp = lin::interp_vf(order, n, true, v, s), qm = lin::interp_vf(order, n, false, v, s + 1);
+    return sign < 0 ? res - qp * up - qm * um : res + qp * up + qm * um;
+}
+
+__global__ void __launch_bounds__(256)
+k_vortex_force_linear(const double* __restrict__ Ux, const double* __restrict__ Uy, const double* __restrict__ Uz,
+                      const double* __restrict__ wx, const double* __restrict__ wy, const double* __restrict__ wz,
+                      double* __restrict__ dux, double* __restrict__ duy, double* __restrict__ duz, int order, Ext e)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int j = blockIdx.y * blockDim.y + threadIdx.y;
+    int k = blockIdx.z * blockDim.z + threadIdx.z;
+    if (i >= e.nx || j >= e.ny || k >= e.nz) return;
+    const long long c = (long long)k * e.sk + (long long)j * e.sj + i;
+    double ax = dux[c], ay = duy[c], az = duz[c];
+    // the three passes "ikj", "jik", "kji" of vortex_force.py:69-81, as in momentum_cell
+    if (i < e.nx - 1) {
+        ax = vf_linear(ax, order, +1, Uy, wz, c, e.sj, 1, j, e.ny);
+        ax = vf_linear(ax, order, -1, Uz, wy, c, e.sk, 1, k, e.nz);
+    }
+    if (j < e.ny - 1) {
+        ay = vf_linear(ay, order, -1, Ux, wz, c, 1, e.sj, i, e.nx);
+        ay = vf_linear(ay, order, +1, Uz, wx, c, e.sk, e.sj, k, e.nz);
+    }
+    if (k < e.nz - 1) {
+        az = vf_linear(az, order, -1, Uy, wx, c, e.sj, e.sk, j, e.ny);
+        az = vf_linear(az, order, +1, Ux, wy, c, 1, e.sk, i, e.nx);
+    }
+    dux[c] = ax; duy[c] = ay; duz[c] = az;
+}
 
 __global__ void __launch_bounds__(256)
 k_add_laplacian(const double* __restrict__ phi, double* __restrict__ dphi, double cx, double cy, double cz, Ext e)
@@ -343,40 +494,10 @@ static int launch_upwind(ny_ctx* ctx, const double* trac, const double* Ux, cons
     if (updp) upd = *updp;
     Ext x = make_ext(e);
     ny_prof_scope ps(ctx, NY_PROF_RHS_TRACER, st);
-    // k_up3 (ny_up3.cuh), the plane-marching TMA kernel that covers the whole array, is bit-identical to k_upwind2 but
-    // NOT faster: 4.07 ms against 4.05 ms per 512^3 launch (both end up at ~1965 MHz and 960-990 W, next to the board's
-    // 1 kW cap; profiles/r2_d_*).  It therefore only runs when asked for (ny_set_momentum_variant(ctx, 2)), which the
-    // parity tests do.
-    bool use3 = !diff && ctx->mom_variant == 2 && (e.nx & 1) == 0;
-    {
-        const void* ptrs[] = {trac, Ux, Uy, Uz};
-        for (const void* p : ptrs) use3 = use3 && (reinterpret_cast<uintptr_t>(p) & 15) == 0;
-    }
-    if (use3) {
-        using namespace u3;
-        Maps tm;
-        int r = ny_tma_encode_3d(&tm.t, trac, e.nx, e.ny, e.nz, PT, TY + 6, 1);
-        if (r == NY_OK) r = ny_tma_encode_3d(&tm.Ux, Ux, e.nx, e.ny, e.nz, PU, TY, 1);
-        if (r == NY_OK) r = ny_tma_encode_3d(&tm.Uy, Uy, e.nx, e.ny, e.nz, PU, TY + 1, 1);
-        if (r == NY_OK) r = ny_tma_encode_3d(&tm.Uz, Uz, e.nx, e.ny, e.nz, PU, TY, 1);
-        if (r != NY_OK) return r;
-        int kchunk = 32;                              // see the note on chunk length in launch_momentum
-        { const char* v = getenv("NY_UP3_KCHUNK"); if (v && atoi(v) > 0) kchunk = atoi(v); }
-        if (kchunk > e.nz) kchunk = e.nz;
-        dim3 grid((e.nx + TX - 1) / TX, (e.ny + TY - 1) / TY, (e.nz + kchunk - 1) / kchunk);
-        static bool attr_set[2] = {false, false};
-        const int fa = ctx->fast_arith ? 1 : 0;
-        if (!attr_set[fa]) {
-            cudaError_t ce = fa ? cudaFuncSetAttribute(k_up3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)
-                                : cudaFuncSetAttribute(k_up3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
-            if (ce != cudaSuccess) { ny_set_error("k_up3: cannot reserve %d bytes of shared memory", SMEM); return NY_ERR_CUDA; }
-            attr_set[fa] = true;
-        }
-        if (fa) k_up3<true><<<grid, NW * 32, SMEM, st>>>(tm, trac, Uz, dtrac, x, kchunk, upd);
-        else k_up3<false><<<grid, NW * 32, SMEM, st>>>(tm, trac, Uz, dtrac, x, kchunk, upd);
-        NY_CHECK_LAUNCH(ctx);
-        return NY_OK;
-    }
+    // (A plane-marching TMA variant of this kernel -- helper warp for the extra faces, pairwise mbarriers, cells
+    // finished one iteration late -- was built, verified bit-identical and measured at 4.07 ms against the 4.05 ms of
+    // this one per 512^3 launch: both sit at 1965 MHz and 960-990 W, next to the 1 kW cap, and the exchange of y fluxes
+    // between the row warps costs what the staging saves.  It was dropped; profiles/r2_d_* keep the record.)
     const int gx = (e.nx + 30) / 31, gy = (e.ny + UP_NW - 2) / (UP_NW - 1);
     // split k so that the launch has ~32 CTAs per SM; each chunk pays one extra plane of z fluxes
     long long want = ((long long)ctx->num_sms * 32 + (long long)gx * gy - 1) / ((long long)gx * gy);
@@ -598,6 +719,36 @@ extern "C" int ny_bernoulli(ny_ctx* ctx, const double* ke, const double* b, doub
     NY_REQUIRE(ctx && ke && dux && duy && duz && (euler || b), "null argument");
     return launch_momentum<true, false, true>(ctx, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, ke, b,
                                               dux, duy, duz, 0.5 * dz, euler ? 0 : 1, e, ny_stream(stream));
+}
+
+// fortran_upwind.upwind with the Fortran's `linear` flag set, for the three directions (tracer.py:44-72):
+// dtrac = -div(U trac) with the linear interpolation of the given order (1..5)
+extern "C" int ny_upwind_linear(ny_ctx* ctx, const double* trac, const double* Ux, const double* Uy, const double* Uz,
+                                double* dtrac, int order, ny_ext e, void* stream)
+{
+    NY_REQUIRE(ctx && trac && Ux && Uy && Uz && dtrac, "null argument");
+    NY_REQUIRE(order >= 1 && order <= 5, "order must be 1..5 (core/interpolate_tracer.f90)");
+    NY_REQUIRE(ext_ok(e), "every extent must be >= 5");
+    ny_grid3 g = ny_cells_launch(e.nz, e.ny, e.nx);
+    ny_prof_scope ps(ctx, NY_PROF_RHS_TRACER, ny_stream(stream));
+    k_upwind_linear<<<g.grid, g.block, 0, ny_stream(stream)>>>(trac, Ux, Uy, Uz, dtrac, order, make_ext(e));
+    NY_CHECK_LAUNCH(ctx);
+    return NY_OK;
+}
+
+// vortex_force.vortex_force with the Fortran's `linear` flag set (accumulates into du, like ny_vortex_force)
+extern "C" int ny_vortex_force_linear(ny_ctx* ctx, const double* Ux, const double* Uy, const double* Uz,
+                                      const double* wx, const double* wy, const double* wz,
+                                      double* dux, double* duy, double* duz, int order, ny_ext e, void* stream)
+{
+    NY_REQUIRE(ctx && Ux && Uy && Uz && wx && wy && wz && dux && duy && duz, "null argument");
+    NY_REQUIRE(order >= 1 && order <= 5, "order must be 1..5 (core/interpolate.f90)");
+    NY_REQUIRE(ext_ok(e), "every extent must be >= 5");
+    ny_grid3 g = ny_cells_launch(e.nz, e.ny, e.nx);
+    ny_prof_scope ps(ctx, NY_PROF_RHS_MOMENTUM, ny_stream(stream));
+    k_vortex_force_linear<<<g.grid, g.block, 0, ny_stream(stream)>>>(Ux, Uy, Uz, wx, wy, wz, dux, duy, duz, order, make_ext(e));
+    NY_CHECK_LAUNCH(ctx);
+    return NY_OK;
 }
 
 extern "C" int ny_add_laplacian(ny_ctx* ctx, const double* phi, double* dphi, double cx, double cy, double cz,

@@ -4,7 +4,10 @@ from .timing import timing
 
 
 class Tracer_numerics(object):
-    def __init__(self, param, grid, traclist, order, diff_coef=[]):
+    def __init__(self, param, grid, traclist, order, diff_coef=[], linear=None):
+        import nyles_b200
+        # the linear branch of fortran_upwind.f90:33-64 instead of WENO (dormant in the shipped reference)
+        self.linear = nyles_b200.LINEAR_UPWIND if linear is None else linear
         self.traclist = traclist
         assert order in {1, 2, 3, 4, 5}
         self.order = order
@@ -26,7 +29,13 @@ class Tracer_numerics(object):
             trac, dtrac = state.get(tracname).tensor, rhs.get(tracname).tensor
             args = (lib.context(trac.device), lib.ptr(trac), lib.ptr(U["i"].tensor), lib.ptr(U["j"].tensor),
                     lib.ptr(U["k"].tensor), lib.ptr(dtrac))
-            if self.diffusion and last and tracname in self.diff_coef:
+            if self.linear:
+                lib.check(L.ny_upwind_linear(*args, int(self.order), lib.ext(trac), lib.stream()))
+                if self.diffusion and last and tracname in self.diff_coef:
+                    c = [self.diff_coef[tracname] * self.ids2[d] for d in "ijk"]
+                    raise NotImplementedError("tracer diffusion with the linear upwind branch (the reference interleaves "
+                                              "the Laplacian between the three sweeps, tracer.py:72-77; coefficients %r)" % c)
+            elif self.diffusion and last and tracname in self.diff_coef:
                 c = [self.diff_coef[tracname] * self.ids2[d] for d in "ijk"]
                 lib.check(L.ny_upwind_diff(*args, c[0], c[1], c[2], lib.ext(trac), lib.stream()))
             else:

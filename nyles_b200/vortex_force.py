@@ -10,10 +10,22 @@ from .timing import timing
 
 
 @timing
-def vortex_force(state, rhs, order):
-    assert order in {1, 2, 3, 4, 5}          # ignored at run time, like the shipped Fortran (linear=.false.)
+def vortex_force(state, rhs, order, linear=None):
+    """rhs.u += vortex force.  `order` is ignored unless the linear branch is on, like the shipped Fortran
+    (linear = .false., fortran_vortex_force.f90:28); linear=None follows nyles_b200.LINEAR_UPWIND."""
+    assert order in {1, 2, 3, 4, 5}
     U, w, du = state.U, state.vor, rhs.u
     t = U["i"].tensor
+    if linear is None:
+        import nyles_b200
+        linear = nyles_b200.LINEAR_UPWIND
+    if linear:
+        lib.check(lib.load().ny_vortex_force_linear(
+            lib.context(t.device), lib.ptr(U["i"].tensor), lib.ptr(U["j"].tensor), lib.ptr(U["k"].tensor),
+            lib.ptr(w["i"].tensor), lib.ptr(w["j"].tensor), lib.ptr(w["k"].tensor),
+            lib.ptr(du["i"].tensor), lib.ptr(du["j"].tensor), lib.ptr(du["k"].tensor),
+            int(order), lib.ext(t), lib.stream()))
+        return
     lib.check(lib.load().ny_vortex_force(
         lib.context(t.device), lib.ptr(U["i"].tensor), lib.ptr(U["j"].tensor), lib.ptr(U["k"].tensor),
         lib.ptr(w["i"].tensor), lib.ptr(w["j"].tensor), lib.ptr(w["k"].tensor),

@@ -119,6 +119,191 @@ static void flux1d(const double *u, const double *q, double *flux, int n)
 
 void orc_flux1d(const double *u, const double *q, double *flux, int n) { flux1d(u, q, flux, n); }
 
+/* ======================================================================
+ * The linear (non-WENO) upwind branch: `linear = .true.` in fortran_upwind.f90:31 and
+ * fortran_vortex_force.f90:28,108.  The reference ships with linear = .false. (the flag is a local
+ * variable, not an argument), so this branch is dormant there; it is restated for SURVEY.md 8(f).4.
+ * Coefficients are REAL(4) constant expressions promoted to double (interpolate.f90:19-33).
+ * ====================================================================== */
+#define LC1 ((double)(-(1.0f / 6.0f)))
+#define LC2 ((double)(5.0f / 6.0f))
+#define LC3 ((double)(2.0f / 6.0f))
+#define LE1 ((double)(-(1.0f / 12.0f)))
+#define LE2 ((double)(7.0f / 12.0f))
+#define LB1 ((double)(2.0f / 60.0f))
+#define LB2 ((double)(-(13.0f / 60.0f)))
+#define LB3 ((double)(47.0f / 60.0f))
+#define LB4 ((double)(27.0f / 60.0f))
+#define LB5 ((double)(-(3.0f / 60.0f)))
+/* 1-based access into 0-based C arrays, as the Fortran writes it */
+#define V1(a, i) ((a)[(i) - 1])
+#define THIRD_P(v, i) (LC1 * V1(v, (i) - 1) + LC2 * V1(v, i) + LC3 * V1(v, (i) + 1))
+#define THIRD_M(v, i) (LC3 * V1(v, (i) - 1) + LC2 * V1(v, i) + LC1 * V1(v, (i) + 1))
+#define FIFTH_P(v, i) (LB1 * V1(v, (i) - 2) + LB2 * V1(v, (i) - 1) + LB3 * V1(v, i) + LB4 * V1(v, (i) + 1) + LB5 * V1(v, (i) + 2))
+#define FIFTH_M(v, i) (LB5 * V1(v, (i) - 2) + LB4 * V1(v, (i) - 1) + LB3 * V1(v, i) + LB2 * V1(v, (i) + 1) + LB1 * V1(v, (i) + 2))
+
+/* core/interpolate.f90:3-112, the flavour included by fortran_vortex_force.f90: qp(0:n-1), qm(1:n).
+ * qp0 points to qp(0); entries the Fortran leaves unassigned keep what the caller put there. */
+static void interpolate_vf(const double *vU, double *qp0, double *qm, int order, int n)
+{
+    int i;
+#define QP(i) qp0[(i)]
+#define QM(i) qm[(i) - 1]
+    if (order == 5) {
+        QP(0) = 0.0;
+        i = 1; QP(i) = V1(vU, i); QM(i) = V1(vU, i);
+        i = 2; QP(i) = THIRD_P(vU, i); QM(i) = THIRD_M(vU, i);
+        for (i = 3; i <= n - 3; i++) { QP(i) = FIFTH_P(vU, i); QM(i) = FIFTH_M(vU, i); }
+        i = n - 2; QP(i) = THIRD_P(vU, i); QM(i) = THIRD_M(vU, i);
+        i = n - 1; QP(i) = V1(vU, i); QM(i) = V1(vU, i);
+        QM(n) = V1(vU, n);
+    } else if (order == 3) {
+        QP(0) = 0.0;
+        i = 1; QP(i) = V1(vU, i); QM(i) = V1(vU, i);
+        for (i = 2; i <= n - 2; i++) { QP(i) = THIRD_P(vU, i); QM(i) = THIRD_M(vU, i); }
+        i = n - 1; QP(i) = V1(vU, i); QM(i) = V1(vU, i);
+        QM(n) = V1(vU, n);
+    } else if (order == 1) {
+        QP(0) = 0.0;
+        for (i = 1; i <= n - 1; i++) { QP(i) = V1(vU, i); QM(i) = V1(vU, i); }
+        QM(n) = V1(vU, n);
+    } else if (order == 2) {
+        QM(1) = 0.5 * V1(vU, 1);
+        for (i = 2; i <= n; i++) QM(i) = 0.5 * (V1(vU, i - 1) + V1(vU, i));
+    } else if (order == 4) {
+        i = 1; QM(i) = LE2 * (V1(vU, i)) + LE1 * (V1(vU, i + 1));
+        i = 2; QM(i) = LE2 * (V1(vU, i - 1) + V1(vU, i)) + LE1 * (V1(vU, i + 1));
+        for (i = 3; i <= n - 1; i++) QM(i) = LE2 * (V1(vU, i - 1) + V1(vU, i)) + LE1 * (V1(vU, i - 2) + V1(vU, i + 1));
+        i = n; QM(i) = LE2 * (V1(vU, i - 1) + V1(vU, i)) + LE1 * (V1(vU, i - 2));
+    }
+#undef QP
+#undef QM
+}
+
+/* core/interpolate_tracer.f90:15-113, the flavour included by fortran_upwind.f90: qp(1:n), qm(1:n) */
+static void interpolate_tr(const double *q, double *qp, double *qm, int order, int n)
+{
+    int i;
+#define QP(i) qp[(i) - 1]
+#define QM(i) qm[(i) - 1]
+    if (order == 5) {
+        i = 1; QP(i) = V1(q, i); QM(i) = V1(q, i);
+        i = 2; QP(i) = THIRD_P(q, i); QM(i) = THIRD_M(q, i);
+        for (i = 3; i <= n - 2; i++) { QP(i) = FIFTH_P(q, i); QM(i) = FIFTH_M(q, i); }
+        i = n - 1; QP(i) = THIRD_P(q, i); QM(i) = THIRD_M(q, i);
+        i = n; QP(i) = V1(q, i); QM(i) = V1(q, i);
+    } else if (order == 3) {
+        i = 1; QP(i) = V1(q, i); QM(i) = V1(q, i);
+        for (i = 2; i <= n - 1; i++) { QP(i) = THIRD_P(q, i); QM(i) = THIRD_M(q, i); }
+        i = n; QP(i) = V1(q, i); QM(i) = V1(q, i);
+    } else if (order == 1) {
+        for (i = 1; i <= n; i++) { QP(i) = V1(q, i); QM(i) = V1(q, i); }
+    } else if (order == 2) {
+        for (i = 1; i <= n - 1; i++) QP(i) = 0.5 * (V1(q, i) + V1(q, i + 1));
+    } else if (order == 4) {
+        i = 1; QP(i) = LE2 * (V1(q, i) + V1(q, i + 1)) + LE1 * (V1(q, i + 2));
+        for (i = 2; i <= n - 2; i++) QP(i) = LE2 * (V1(q, i) + V1(q, i + 1)) + LE1 * (V1(q, i - 1) + V1(q, i + 2));
+        i = n - 1; QP(i) = LE2 * (V1(q, i) + V1(q, i + 1)) + LE1 * (V1(q, i - 1));
+    }
+#undef QP
+#undef QM
+}
+
+void orc_interpolate_vf(const double *vU, double *qp0, double *qm, int order, int n) { interpolate_vf(vU, qp0, qm, order, n); }
+void orc_interpolate_tr(const double *q, double *qp, double *qm, int order, int n) { interpolate_tr(q, qp, qm, order, n); }
+
+/* fortran_upwind.f90:33-64, the branch `if (linear)` */
+void orc_upwind_linear(const double *trac, const double *u, double *dtrac, int order,
+                       int l, int m, int n, const ptrdiff_t *s)
+{
+#pragma omp parallel
+    {
+        double *up = calloc(5 * (size_t)n, sizeof(double));
+        double *um = up + n, *phi = up + 2 * n, *qp = up + 3 * n, *qm = up + 4 * n;
+#pragma omp for collapse(2)
+        for (int k = 0; k < l; k++)
+            for (int j = 0; j < m; j++) {
+                for (int i = 0; i < n; i++) {
+                    const double ui = AT(u, s, k, j, i), UU = fabs(ui);
+                    up[i] = 0.5 * (ui + UU);
+                    um[i] = 0.5 * (ui - UU);
+                    phi[i] = AT(trac, s, k, j, i);
+                }
+                interpolate_tr(phi, qp, qm, order, n);
+                double fxm = 0.0, fx;
+                for (int i = 0; i < n - 1; i++) {
+                    if (order % 2 == 0) fx = AT(u, s, k, j, i) * qp[i];
+                    else fx = up[i] * qp[i] + um[i] * qm[i + 1];
+                    AT(dtrac, s, k, j, i) = AT(dtrac, s, k, j, i) + fxm - fx;
+                    fxm = fx;
+                }
+                fx = 0.0;
+                AT(dtrac, s, k, j, n - 1) = AT(dtrac, s, k, j, n - 1) + fxm - fx;
+            }
+        free(up);
+    }
+}
+
+/* fortran_vortex_force.f90:39-64, the branch `if (linear)` of vortex_force_direc */
+void orc_vortex_force_direc_linear(const double *U, const double *vort, double *res, int order,
+                                   int m, int n, int l, const ptrdiff_t *s)
+{
+#pragma omp parallel
+    {
+        double *vU = calloc(5 * (size_t)l + 1, sizeof(double));
+        double *up = vU + l, *um = vU + 2 * l, *qm = vU + 3 * l, *qp0 = vU + 4 * l;   /* qp(0:l-1) */
+#pragma omp for collapse(2)
+        for (int j = 0; j < m; j++)
+            for (int i = 0; i < n - 1; i++) {
+                double UU_0 = 0.0;
+                for (int k = 0; k < l; k++) {
+                    const double UU_1 = 0.5 * (AT(U, s, j, i, k) + AT(U, s, j, i + 1, k));
+                    vU[k] = AT(vort, s, j, i, k);
+                    const double Ui = 0.5 * (UU_0 + UU_1), UU = fabs(Ui);
+                    up[k] = 0.5 * (Ui + UU);
+                    um[k] = 0.5 * (Ui - UU);
+                    UU_0 = UU_1;
+                }
+                interpolate_vf(vU, qp0, qm, order, l);
+                for (int k = 0; k < l; k++) {            /* Fortran k = k+1: qp(k-1) -> qp0[k], qm(k) -> qm[k] */
+                    if (order % 2 == 0) AT(res, s, j, i, k) = AT(res, s, j, i, k) - qm[k];
+                    else AT(res, s, j, i, k) = AT(res, s, j, i, k) - qp0[k] * up[k] - qm[k] * um[k];
+                }
+            }
+        free(vU);
+    }
+}
+
+/* fortran_vortex_force.f90:118-143, the branch `if (linear)` of vortex_force_flip */
+void orc_vortex_force_flip_linear(const double *U, const double *vort, double *res, int order,
+                                  int m, int n, int l, const ptrdiff_t *s)
+{
+#pragma omp parallel
+    {
+        double *vU = calloc(5 * (size_t)n + 1, sizeof(double));
+        double *up = vU + n, *um = vU + 2 * n, *qm = vU + 3 * n, *qp0 = vU + 4 * n;
+#pragma omp for collapse(2)
+        for (int j = 0; j < m; j++)
+            for (int k = 0; k < l - 1; k++) {
+                double UU_0 = 0.0;
+                for (int i = 0; i < n; i++) {
+                    const double UU_1 = 0.5 * (AT(U, s, j, i, k) + AT(U, s, j, i, k + 1));
+                    vU[i] = AT(vort, s, j, i, k);
+                    const double Ui = 0.5 * (UU_0 + UU_1), UU = fabs(Ui);
+                    up[i] = 0.5 * (Ui + UU);
+                    um[i] = 0.5 * (Ui - UU);
+                    UU_0 = UU_1;
+                }
+                interpolate_vf(vU, qp0, qm, order, n);
+                for (int i = 0; i < n; i++) {
+                    if (order % 2 == 0) AT(res, s, j, i, k) = AT(res, s, j, i, k) + qm[i];
+                    else AT(res, s, j, i, k) = AT(res, s, j, i, k) + qp0[i] * up[i] + qm[i] * um[i];
+                }
+            }
+        free(vU);
+    }
+}
+
 /* ---- core/fortran_vorticity.f90:2-28 ----------------------------------- */
 void orc_vorticity(const double *ui, const double *uj, double *wk,
                    int l, int m, int n, const ptrdiff_t *s)

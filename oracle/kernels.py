@@ -80,16 +80,42 @@ class Kernels(object):
         assert n >= 5
         self.L.orc_upwind(_p(trac), _p(u), _p(dtrac), l, m, n, st)
 
-    # fortran_vortex_force.vortex_force_direc / _flip (U, vort, res, order)
-    def vortex_force_direc(self, U, vort, res, order=5):
+    # fortran_vortex_force.vortex_force_direc / _flip (U, vort, res, order).  linear=True: the branch the Fortran
+    # takes when its local flag `linear` is .true. (dormant in the reference as shipped)
+    def vortex_force_direc(self, U, vort, res, order=5, linear=False):
         (m, n, l), st = _common([U, vort, res])
         assert l >= 5
-        self.L.orc_vortex_force_direc(_p(U), _p(vort), _p(res), m, n, l, st)
+        if linear:
+            self.L.orc_vortex_force_direc_linear(_p(U), _p(vort), _p(res), int(order), m, n, l, st)
+        else:
+            self.L.orc_vortex_force_direc(_p(U), _p(vort), _p(res), m, n, l, st)
 
-    def vortex_force_flip(self, U, vort, res, order=5):
+    def vortex_force_flip(self, U, vort, res, order=5, linear=False):
         (m, n, l), st = _common([U, vort, res])
         assert n >= 5
-        self.L.orc_vortex_force_flip(_p(U), _p(vort), _p(res), m, n, l, st)
+        if linear:
+            self.L.orc_vortex_force_flip_linear(_p(U), _p(vort), _p(res), int(order), m, n, l, st)
+        else:
+            self.L.orc_vortex_force_flip(_p(U), _p(vort), _p(res), m, n, l, st)
+
+    def upwind_linear(self, trac, u, dtrac, order):
+        (l, m, n), st = _common([trac, u, dtrac])
+        assert n >= 5
+        self.L.orc_upwind_linear(_p(trac), _p(u), _p(dtrac), int(order), l, m, n, st)
+
+    def interpolate_vf(self, vU, order):
+        """core/interpolate.f90 (vortex-force flavour): returns (qp(0:n-1), qm(1:n)), unassigned entries NaN."""
+        vU = np.ascontiguousarray(vU, dtype=np.float64)
+        qp, qm = np.full(len(vU), np.nan), np.full(len(vU), np.nan)
+        self.L.orc_interpolate_vf(_p(vU), _p(qp), _p(qm), int(order), len(vU))
+        return qp, qm
+
+    def interpolate_tr(self, q, order):
+        """core/interpolate_tracer.f90: returns (qp(1:n), qm(1:n)), unassigned entries NaN."""
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        qp, qm = np.full(len(q), np.nan), np.full(len(q), np.nan)
+        self.L.orc_interpolate_tr(_p(q), _p(qp), _p(qm), int(order), len(q))
+        return qp, qm
 
     # fortran_kinenergy.kin(u, v, ke, ds2, order)
     def kin(self, u, v, ke, ds2, order=2):

@@ -215,15 +215,15 @@ def vorticity(K, state, fparameter):
             wk[:, :-1, :-1] += fparameter
 
 
-def vortex_force(K, state, rhs, order=5):
+def vortex_force(K, state, rhs, order=5, linear=False):
     for k, j, i in ["ikj", "jik", "kji"]:
         u_i = rhs.u[i].flipview(j)
         u_k = rhs.u[k].flipview(j)
         U_i = state.U[i].flipview(j)
         U_k = state.U[k].flipview(j)
         w_j = state.vor[j].flipview(j)
-        K.vortex_force_direc(U_k, w_j, u_i, order)
-        K.vortex_force_flip(U_i, w_j, u_k, order)
+        K.vortex_force_direc(U_k, w_j, u_i, order, linear=linear)
+        K.vortex_force_flip(U_i, w_j, u_k, order, linear=linear)
 
 
 def kinenergy(K, state, grid, order=2):
@@ -245,7 +245,7 @@ def bernoulli(K, state, rhs, grid, euler=False):
             K.gradkeandb(ke, state.b.view(d), du, grid.dz)
 
 
-def rhstrac(K, state, rhs, traclist, order=5, diff_coef=None, ids2=None, last=False):
+def rhstrac(K, state, rhs, traclist, order=5, diff_coef=None, ids2=None, last=False, linear=False):
     for name in traclist:
         trac, dtrac = state.get(name), rhs.get(name)
         for d in "ijk":
@@ -253,7 +253,10 @@ def rhstrac(K, state, rhs, traclist, order=5, diff_coef=None, ids2=None, last=Fa
             field, dfield = trac.view(d), dtrac.view(d)
             if d == "i":
                 dfield[...] = 0.0
-            K.upwind(field, vel, dfield, order)
+            if linear:
+                K.upwind_linear(field, vel, dfield, order)
+            else:
+                K.upwind(field, vel, dfield, order)
             if diff_coef and last and name in diff_coef:
                 K.add_laplacian(field, dfield, diff_coef[name] * ids2[d])
 
@@ -297,9 +300,11 @@ def vf_work(K, state, dstate, work, domainindices):
 class LES(object):
     """model_les.LES / model_les_euler.LES (modelname 'LES' | 'Euler3d' | 'linear')."""
 
-    def __init__(self, param, flavour="strict"):
+    def __init__(self, param, flavour="strict", linear_upwind=False):
         self.K = Kernels(flavour)
         self.param = param
+        # the Fortran's local flag `linear` (fortran_upwind.f90:31, fortran_vortex_force.f90:28,108); .false. as shipped
+        self.linear_upwind = linear_upwind
         self.modelname = param.get("modelname", "LES")
         self.euler = self.modelname == "Euler3d"
         self.nonlinear = self.modelname != "linear"
@@ -344,9 +349,10 @@ class LES(object):
         if not self.euler:
             # model_les.py:133 calls rhstrac(state, dstate) without `last`, so tracer
             # diffusion (tracer.py:74-77) is never active in the LES model
-            rhstrac(K, state, dstate, self.traclist, diff_coef=self.diff_coef, ids2=self.grid.ids2, last=False)
+            rhstrac(K, state, dstate, self.traclist, order=self.param.get("orderA", 5), diff_coef=self.diff_coef,
+                    ids2=self.grid.ids2, last=False, linear=self.linear_upwind)
         if self.nonlinear:
-            vortex_force(K, state, dstate)
+            vortex_force(K, state, dstate, order=self.param.get("orderVF", 5), linear=self.linear_upwind)
         bernoulli(K, state, dstate, self.grid, euler=self.euler)
         if last and "u" in self.diff_coef:
             add_viscosity(K, self.grid, state, dstate, self.diff_coef["u"])

@@ -219,6 +219,39 @@ def test_views_survive_the_buffer_rotation_and_passive_tracers_follow():
     assert float(st.u["i"].tensor.abs().max()) > 0
 
 
+@pytest.mark.parametrize("shape", [(32, 16, 16), (16, 64, 32)])
+def test_merged_projection_and_diagnostics_pass_is_bit_identical(shape):
+    """Closed box, one rank: diagnose_var writes p, the projected u, U, vorticity, kinetic energy and max|U|^2 in ONE
+    pass after the solve (ny_mg_project_post) instead of two (ny_mg_project + ny_diag_post).  Same statements,
+    same bits -- every field, dt and V-cycle count over a few steps."""
+    nz, ny_, nx = shape
+    kw = dict(nx=nx, ny=ny_, nz=nz, geometry="closed", Lx=nx / 8.0, Ly=ny_ / 8.0, Lz=nz / 8.0, cfl=0.8, dt_max=0.05)
+    runs = []
+    for merged in (True, False):
+        ny = make_nyles(kw)
+        ny.model.merge_projection = merged
+        rng = np.random.default_rng(11)
+        st = ny.model.state
+        st.b.view("i")[:] = np.tanh(rng.standard_normal((nz, ny_, nx)))
+        for d in "ijk":
+            st.u[d].view("i")[:] = 0.02 * rng.standard_normal((nz, ny_, nx))
+        ny.model.diagnose_var(st)
+        t, log = 0.0, []
+        for n in range(4):
+            dt = ny.compute_dt()
+            ny.model.forward(t, dt)
+            t += dt
+            log.append((dt, ny.model.mg.stats["nite"]))
+        fields = {s: getattr(st, s).tensor.clone() for s in SCALARS}
+        for v in VECTORS:
+            for d in "ijk":
+                fields[v + d] = getattr(st, v)[d].tensor.clone()
+        runs.append((log, fields))
+    assert runs[0][0] == runs[1][0]
+    for name in runs[0][1]:
+        assert torch.equal(runs[0][1][name], runs[1][1][name]), name
+
+
 def test_step_host_honours_edited_host_buffers():
     """step_host(modified=True): the caller has edited the host buffers, so the upload must be followed by
     diagnose_var and an Euler start-up step, as a run that begins from that state does (core/nyles.py:125,

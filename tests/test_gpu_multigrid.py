@@ -192,8 +192,12 @@ def test_fused_legs_equal_single_operator_kernels(grid, split):
     from nyles_b200.mgfordriver import MG
     from nyles_b200 import lib
     nx, ny, nz, topo = grid
-    lib.load().ny_mg_set_split_tiles(1)            # test grids are small: split wherever a wall-free tile exists
-    fused, plain = MG(1, 1, nx, ny, nz, 3, topo), MG(1, 1, nx, ny, nz, 3, topo)
+    # test grids are small: split wherever a wall-free tile exists (a default that multigrids copy at creation)
+    lib.load().ny_mg_set_split_tiles(1)
+    try:
+        fused, plain = MG(1, 1, nx, ny, nz, 3, topo), MG(1, 1, nx, ny, nz, 3, topo)
+    finally:
+        lib.load().ny_mg_set_split_tiles(148)
     plain.set_fused_legs(False)
     # split 1 (default): tiles away from the x / y walls run the specialised (wall-free) kernel instance,
     # the frame around them the general one; split 2: every tile through the general instance
@@ -223,7 +227,6 @@ def test_fused_legs_equal_single_operator_kernels(grid, split):
         assert fused.stats["nite"] == plain.stats["nite"] and fused.stats["nite"] > 0
         np.testing.assert_allclose(fused.stats["res"], plain.stats["res"], rtol=1e-11, atol=0)
         assert torch.equal(xf, xp)
-    lib.load().ny_mg_set_split_tiles(148)
 
 
 @pytest.mark.parametrize("grid", [(32, 16, 16, 1), (16, 16, 16, 6), (16, 32, 8, 5)])

@@ -84,9 +84,9 @@ def oracle_upwind(K, trac, U, coefs=None):
 # --------------------------------------------------------------------------- tests
 @pytest.fixture(params=[1, 2], ids=["cellwise", "tma_marching"])
 def mom_variant(request, L):
-    """Which kernels evaluate the WENO right-hand sides: the cell-parallel ones (k_momentum, k_upwind2) or the
-    plane-marching ones with TMA-staged tiles (k_mom3 for the interior of the momentum equations, k_up3 for the
-    tracer; they need an even nx and are otherwise only chosen for large grids).  Both must be bit-identical."""
+    """Which kernel evaluates the interior cells of the fused momentum right-hand side: k_momentum (one thread per
+    cell) or k_mom3 (plane marching, TMA-staged tiles; needs an even nx and is otherwise only chosen for large
+    grids).  Both must be bit-identical."""
     L.check(L.load().ny_set_momentum_variant(L.context(), request.param))
     yield request.param
     L.check(L.load().ny_set_momentum_variant(L.context(), 0))
@@ -147,7 +147,7 @@ def test_kin_div_gradp_scale(K, L, shape):
 
 @pytest.mark.parametrize("shape", SHAPES + [(40, 37, 70), (9, 70, 34), (37, 19, 66)])
 @pytest.mark.parametrize("seed", [10, 11])
-def test_upwind(K, L, shape, seed, mom_variant):
+def test_upwind(K, L, shape, seed):
     trac, Ux, Uy, Uz = rand_fields(shape, 4, seed)
     ref = oracle_upwind(K, trac, [Ux, Uy, Uz])
     g = [dev(a) for a in (trac, Ux, Uy, Uz)]
@@ -161,7 +161,7 @@ def test_upwind(K, L, shape, seed, mom_variant):
     assert np.array_equal(ref, host(out))
 
 
-def test_upwind_smooth_and_zero_velocity(K, L, mom_variant):
+def test_upwind_smooth_and_zero_velocity(K, L):
     """sign test is strictly u > 0 (weno.f90:114): zero and negative-zero velocities take the else branch."""
     shape = (8, 9, 12)
     z, y, x = np.meshgrid(*[np.linspace(0, 1, n) for n in shape], indexing="ij")

@@ -551,3 +551,170 @@ def test_mg_operators_equal_independent_numpy_transcription(topology):
     if per:
         _wrap(xf, nh, 1, 1, 1)
     assert np.array_equal(mg.get_array(ivar=1), xf)
+
+
+# ---------------------------------------------------------------- the linear (non-WENO) upwind branch
+# Second, independent transcription (plain Python loops, straight from the Fortran) of core/interpolate.f90,
+# core/interpolate_tracer.f90 and of the `if (linear)` branches of fortran_upwind.f90:33-64 and
+# fortran_vortex_force.f90:39-64,118-143; must agree with the C restatement bit for bit.
+_f32 = np.float32
+_LC = [float(-(_f32(1.) / _f32(6.))), float(_f32(5.) / _f32(6.)), float(_f32(2.) / _f32(6.))]
+_LE = [float(-(_f32(1.) / _f32(12.))), float(_f32(7.) / _f32(12.))]
+_LB = [float(_f32(2.) / _f32(60.)), float(-(_f32(13.) / _f32(60.))), float(_f32(47.) / _f32(60.)),
+       float(_f32(27.) / _f32(60.)), float(-(_f32(3.) / _f32(60.)))]
+
+
+def _py_interpolate(v, order, tracer):
+    """Returns dicts qp, qm keyed by the Fortran index."""
+    n = len(v)
+    q = lambda i: v[i - 1]                         # noqa: E731
+    c1, c2, c3 = _LC
+    e1, e2 = _LE
+    b1, b2, b3, b4, b5 = _LB
+    qp, qm = {}, {}
+
+    def third(i):
+        qp[i] = c1 * q(i - 1) + c2 * q(i) + c3 * q(i + 1)
+        qm[i] = c3 * q(i - 1) + c2 * q(i) + c1 * q(i + 1)
+
+    def fifth(i):
+        qp[i] = b1 * q(i - 2) + b2 * q(i - 1) + b3 * q(i) + b4 * q(i + 1) + b5 * q(i + 2)
+        qm[i] = b5 * q(i - 2) + b4 * q(i - 1) + b3 * q(i) + b2 * q(i + 1) + b1 * q(i + 2)
+
+    def copy(i):
+        qp[i] = q(i); qm[i] = q(i)
+    if tracer:                                     # interpolate_tracer.f90
+        if order == 5:
+            copy(1); third(2)
+            for i in range(3, n - 1):
+                fifth(i)
+            third(n - 1); copy(n)
+        elif order == 3:
+            copy(1)
+            for i in range(2, n):
+                third(i)
+            copy(n)
+        elif order == 1:
+            for i in range(1, n + 1):
+                copy(i)
+        elif order == 2:
+            for i in range(1, n):
+                qp[i] = 0.5 * (q(i) + q(i + 1))
+        elif order == 4:
+            qp[1] = e2 * (q(1) + q(2)) + e1 * (q(3))
+            for i in range(2, n - 1):
+                qp[i] = e2 * (q(i) + q(i + 1)) + e1 * (q(i - 1) + q(i + 2))
+            i = n - 1
+            qp[i] = e2 * (q(i) + q(i + 1)) + e1 * (q(i - 1))
+    else:                                          # interpolate.f90
+        if order == 5:
+            qp[0] = 0.0
+            copy(1); third(2)
+            for i in range(3, n - 2):
+                fifth(i)
+            third(n - 2); copy(n - 1)
+            qm[n] = q(n)
+        elif order == 3:
+            qp[0] = 0.0
+            copy(1)
+            for i in range(2, n - 1):
+                third(i)
+            copy(n - 1)
+            qm[n] = q(n)
+        elif order == 1:
+            qp[0] = 0.0
+            for i in range(1, n):
+                copy(i)
+            qm[n] = q(n)
+        elif order == 2:
+            qm[1] = 0.5 * q(1)
+            for i in range(2, n + 1):
+                qm[i] = 0.5 * (q(i - 1) + q(i))
+        elif order == 4:
+            qm[1] = e2 * (q(1)) + e1 * (q(2))
+            qm[2] = e2 * (q(1) + q(2)) + e1 * (q(3))
+            for i in range(3, n):
+                qm[i] = e2 * (q(i - 1) + q(i)) + e1 * (q(i - 2) + q(i + 1))
+            qm[n] = e2 * (q(n - 1) + q(n)) + e1 * (q(n - 2))
+    return qp, qm
+
+
+@pytest.mark.parametrize("order", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("n", [5, 6, 7, 12])
+def test_linear_interpolations_second_transcription(order, n):
+    rng = np.random.default_rng(100 + order + n)
+    v = rng.standard_normal(n) * 10.0 ** rng.integers(-3, 4)
+    for tracer in (False, True):
+        qp, qm = _py_interpolate(v, order, tracer)
+        cp, cm = (K.interpolate_tr if tracer else K.interpolate_vf)(v, order)
+        for i, val in qp.items():
+            got = cp[i - 1] if tracer else cp[i]          # the vortex-force flavour stores qp(0:n-1)
+            assert got == val, (tracer, "qp", i)
+        for i, val in qm.items():
+            assert cm[i - 1] == val, (tracer, "qm", i)
+        # nothing else is assigned
+        assert np.count_nonzero(~np.isnan(cp)) == len(qp) and np.count_nonzero(~np.isnan(cm)) == len(qm)
+
+
+@pytest.mark.parametrize("order", [1, 2, 3, 4, 5])
+def test_linear_upwind_and_vortex_force_second_transcription(order):
+    rng = np.random.default_rng(200 + order)
+    l, m, n = 3, 4, 9
+    trac, u = rng.standard_normal((l, m, n)), rng.standard_normal((l, m, n))
+    d0 = rng.standard_normal((l, m, n))
+    ref = d0.copy()
+    for k in range(l):
+        for j in range(m):
+            up = [0.5 * (x + abs(x)) for x in u[k, j]]
+            um = [0.5 * (x - abs(x)) for x in u[k, j]]
+            qp, qm = _py_interpolate(trac[k, j], order, True)
+            fxm = 0.0
+            for i in range(1, n):
+                fx = u[k, j, i - 1] * qp[i] if order % 2 == 0 else up[i - 1] * qp[i] + um[i - 1] * qm[i + 1]
+                ref[k, j, i - 1] = ref[k, j, i - 1] + fxm - fx
+                fxm = fx
+            ref[k, j, n - 1] = ref[k, j, n - 1] + fxm - 0.0
+    got = d0.copy()
+    K.upwind_linear(trac, u, got, order)
+    assert np.array_equal(got, ref)
+    # vortex_force_direc / _flip, arrays (m, n, l) = [j, i, k]
+    m, n, l = 3, 7, 8
+    U, w, r0 = (rng.standard_normal((m, n, l)) for _ in range(3))
+    ref = r0.copy()
+    for j in range(m):
+        for i in range(n - 1):
+            UU_0, vU, up, um = 0.0, [], [], []
+            for k in range(l):
+                UU_1 = 0.5 * (U[j, i, k] + U[j, i + 1, k])
+                vU.append(w[j, i, k])
+                Ui = 0.5 * (UU_0 + UU_1)
+                up.append(0.5 * (Ui + abs(Ui))); um.append(0.5 * (Ui - abs(Ui)))
+                UU_0 = UU_1
+            qp, qm = _py_interpolate(np.array(vU), order, False)
+            for k in range(1, l + 1):
+                if order % 2 == 0:
+                    ref[j, i, k - 1] = ref[j, i, k - 1] - qm[k]
+                else:
+                    ref[j, i, k - 1] = ref[j, i, k - 1] - qp[k - 1] * up[k - 1] - qm[k] * um[k - 1]
+    got = r0.copy()
+    K.vortex_force_direc(U, w, got, order, linear=True)
+    assert np.array_equal(got, ref)
+    ref = r0.copy()
+    for j in range(m):
+        for k in range(l - 1):
+            UU_0, vU, up, um = 0.0, [], [], []
+            for i in range(n):
+                UU_1 = 0.5 * (U[j, i, k] + U[j, i, k + 1])
+                vU.append(w[j, i, k])
+                Ui = 0.5 * (UU_0 + UU_1)
+                up.append(0.5 * (Ui + abs(Ui))); um.append(0.5 * (Ui - abs(Ui)))
+                UU_0 = UU_1
+            qp, qm = _py_interpolate(np.array(vU), order, False)
+            for i in range(1, n + 1):
+                if order % 2 == 0:
+                    ref[j, i - 1, k] = ref[j, i - 1, k] + qm[i]
+                else:
+                    ref[j, i - 1, k] = ref[j, i - 1, k] + qp[i - 1] * up[i - 1] + qm[i] * um[i - 1]
+    got = r0.copy()
+    K.vortex_force_flip(U, w, got, order, linear=True)
+    assert np.array_equal(got, ref)
