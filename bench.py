@@ -279,8 +279,6 @@ def family_bytes_per_cell(euler):
         "rhs_momentum": (56.0 if euler else 64.0) + 36.0 + 24.0,
         "vorticity_ke": 40.0,                     # vorticity: u x3 -> vor x3 (48); ke: u x3 -> ke (32); mean per group
         "div": 32.0, "gradp": 56.0, "U_from_u": 48.0,
-        # merged "u -= grad p" + U + vorticity + kinetic energy: x, u x3 read; p, u x3, U x3, vor x3, ke written
-        "gradp_vorticity_ke": 120.0,
         "timescheme": 36.0,                       # predictor 48, corrector 24 per field; mean per group
         "maxspeed": 24.0,
         "mg_smooth_fine": 24.0,                   # x, b -> x (two Jacobi sweeps fused in one pass)

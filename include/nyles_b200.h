@@ -72,7 +72,6 @@ enum { NY_PROF_RHS_TRACER = 0, NY_PROF_RHS_MOMENTUM, NY_PROF_VORT_KE, NY_PROF_DI
        NY_PROF_MG_PROLONG_FINE, NY_PROF_MG_NORM, NY_PROF_MG_COARSE, NY_PROF_MG_EMBED,
        NY_PROF_MG_DOWN_FINE,   /* fused smooth + residual + restriction of level 1 */
        NY_PROF_MG_UP_FINE,     /* fused prolongation + smooth (+ residual norm) of level 1 */
-       NY_PROF_GRADP_POST,     /* u -= grad p fused with U, vorticity, kinetic energy (ny_mg_project_post) */
        NY_PROF_NTAGS };
 
 /* ---- context ---------------------------------------------------------------------- */
@@ -299,14 +298,6 @@ int  ny_mg_solve_directly(ny_mg*, double* p, const double* div, ny_ext e, const 
 int  ny_mg_project(ny_mg*, double* ux, double* uy, double* uz, double* div, double* p,
                    double idx2, double idy2, double idz2, ny_ext e, const int lo[3], double scale,
                    ny_mg_stats* stats_host, void* stream);
-/* ny_mg_project followed by ny_diag_post with the two passes over u merged (15 arrays through HBM instead of 18):
- * the projected velocity is written to uo[] (must not alias u[]), which the caller then uses as u.  Only for domains
- * whose u needs no halo refresh between the projection and the diagnostics (closed box, one rank). */
-int  ny_mg_project_post(ny_mg*, const double* ux, const double* uy, const double* uz,
-                        double* uxo, double* uyo, double* uzo, double* div, double* p,
-                        double* Ux, double* Uy, double* Uz, double* wx, double* wy, double* wz, double* ke,
-                        double idx2, double idy2, double idz2, double fparam, ny_ext e, const int lo[3],
-                        double scale, ny_mg_stats* stats_host, void* stream);
 int  ny_mg_op(ny_mg*, int op, int lev, void* stream);
 
 /* ---- the linear (non-WENO) upwind branch ---------------------------------------------------------

@@ -71,7 +71,7 @@ extern "C" void ny_launch_count_reset(ny_ctx* ctx) { if (ctx) ctx->launches = 0;
 static const char* const g_prof_names[NY_PROF_NTAGS] = {
     "rhs_tracer", "rhs_momentum", "vorticity_ke", "div", "gradp", "U_from_u", "timescheme", "maxspeed",
     "halo", "mg_smooth_fine", "mg_residual_fine", "mg_restrict_fine", "mg_prolong_fine", "mg_norm",
-    "mg_coarse_levels", "mg_embed_extract", "mg_down_fine", "mg_up_fine", "gradp_vorticity_ke"};
+    "mg_coarse_levels", "mg_embed_extract", "mg_down_fine", "mg_up_fine"};
 
 extern "C" const char* ny_prof_name(int tag)
 {

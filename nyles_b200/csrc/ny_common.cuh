@@ -84,8 +84,3 @@ static inline ny_grid3 ny_cells_launch(int nz, int ny, int nx, int bx = 32, int 
     return g;
 }
 
-// ny_diag.cu: u -= grad p fused with U, vorticity, kinetic energy and max|U|^2 (called by ny_mg_project_post)
-int ny_launch_gradp_post(ny_ctx* ctx, const double* xmg, long long msj, long long msk, long long m0, double scale,
-                         const double* ux, const double* uy, const double* uz, double* p, double* uxo, double* uyo, double* uzo,
-                         double* Ux, double* Uy, double* Uz, double* wx, double* wy, double* wz, double* ke,
-                         double idx2, double idy2, double idz2, double fparam, ny_ext e, cudaStream_t st);

@@ -5,6 +5,7 @@
 // (core/projection.py:16-29,84-87), core/cov_to_contra.py:4-20, the NumPy updates of
 // core/timescheme.py:113-221, core/nyles.py:244-250 and core/mpi/halo.py:140-178.
 #include "ny_common.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -109,92 +110,6 @@ k_diag_post(const double* __restrict__ ux, const double* __restrict__ uy, const 
     if (i > 0) { double q = ux[c - 1]; acc = acc + cx * (u0 * u0 + q * q); }
     if (j > 0) { double q = uy[c - e.sj]; acc = acc + cy * (v0 * v0 + q * q); }
     if (k > 0) { double q = uz[c - e.sk]; acc = acc + cz * (w0 * w0 + q * q); }
-    ke[c] = acc;
-}
-
-// compute_p's "u -= delta p" (core/projection.py:84-87, fortran_bernoulli.f90:2-26) together with everything that
-// diagnose_var derives from the projected velocity (core/model_les.py:112-123: U_from_u, vorticity, kinenergy) in
-// ONE pass: p = x * scale, the projected u goes to SEPARATE arrays (a cell's neighbours still read the old u), and
-// U, vor, ke, max|U|^2 are evaluated from projected values that each thread recomputes for the 12 neighbour
-// components it needs -- the same expression u - (p(s+1) - p(s)) wherever it is evaluated, so the bits are those of
-// k_extract_gradp followed by k_diag_post.  15 arrays instead of 18 move through HBM per projection.
-struct GpIn {
-    const double* x;                 // level-1 solution of the multigrid (padded array)
-    long long msj, msk;              // its row / plane strides
-    long long m0;                    // offset of the model array's cell (0,0,0) inside it
-    const double *ux, *uy, *uz;      // velocity before the projection
-    double scale;
-};
-
-__device__ __forceinline__ double gp_p(const GpIn& a, int k, int j, int i)
-{
-    return a.x[a.m0 + (long long)k * a.msk + (long long)j * a.msj + i] * a.scale;
-}
-// projected velocity component at cell (k, j, i); cells on the last index of the component's own axis keep u
-__device__ __forceinline__ double gp_ux(const GpIn& a, const Ext& e, int k, int j, int i)
-{
-    const double u = a.ux[(long long)k * e.sk + (long long)j * e.sj + i];
-    return i < e.nx - 1 ? u - (gp_p(a, k, j, i + 1) - gp_p(a, k, j, i)) : u;
-}
-__device__ __forceinline__ double gp_uy(const GpIn& a, const Ext& e, int k, int j, int i)
-{
-    const double u = a.uy[(long long)k * e.sk + (long long)j * e.sj + i];
-    return j < e.ny - 1 ? u - (gp_p(a, k, j + 1, i) - gp_p(a, k, j, i)) : u;
-}
-__device__ __forceinline__ double gp_uz(const GpIn& a, const Ext& e, int k, int j, int i)
-{
-    const double u = a.uz[(long long)k * e.sk + (long long)j * e.sj + i];
-    return k < e.nz - 1 ? u - (gp_p(a, k + 1, j, i) - gp_p(a, k, j, i)) : u;
-}
-
-__global__ void __launch_bounds__(256)
-k_gradp_post(GpIn a, double* __restrict__ p, double* __restrict__ uxo, double* __restrict__ uyo, double* __restrict__ uzo,
-             double* __restrict__ Ux, double* __restrict__ Uy, double* __restrict__ Uz,
-             double* __restrict__ wx, double* __restrict__ wy, double* __restrict__ wz, double* __restrict__ ke,
-             double idx2, double idy2, double idz2, double cx, double cy, double cz, double fparam, Ext e,
-             unsigned long long* __restrict__ maxbits)
-{
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int j = blockIdx.y * blockDim.y + threadIdx.y;
-    int k = blockIdx.z * blockDim.z + threadIdx.z;
-    const bool inside = i < e.nx && j < e.ny && k < e.nz;
-    unsigned long long qb = 0ull;
-    const long long c = (long long)k * e.sk + (long long)j * e.sj + i;
-    double u0 = 0.0, v0 = 0.0, w0 = 0.0;
-    if (inside) {
-        p[c] = gp_p(a, k, j, i);
-        u0 = gp_ux(a, e, k, j, i); v0 = gp_uy(a, e, k, j, i); w0 = gp_uz(a, e, k, j, i);
-        uxo[c] = u0; uyo[c] = v0; uzo[c] = w0;
-        const double U0 = u0 * idx2, V0 = v0 * idy2, W0 = w0 * idz2;
-        Ux[c] = U0; Uy[c] = V0; Uz[c] = W0;
-        const double q = U0 * U0 + V0 * V0 + W0 * W0;
-        qb = (q == q) ? (unsigned long long)__double_as_longlong(q) : 0x7ff8000000000000ull;
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long other = __shfl_xor_sync(0xffffffffu, qb, o);
-        qb = other > qb ? other : qb;
-    }
-    if ((threadIdx.x & 31) == 0) {
-        const unsigned slot = ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8u +
-                              ((threadIdx.z * blockDim.y + threadIdx.y) * blockDim.x + threadIdx.x) / 32u;
-        atomicMax(maxbits + (slot & (NY_MAX_SLOTS - 1)), qb);
-    }
-    if (!inside) return;
-    // the statements of k_diag_post on the projected velocity
-    const bool ip = i < e.nx - 1, jp = j < e.ny - 1, kp = k < e.nz - 1;
-    if (kp) wx[c] = jp ? gp_uz(a, e, k, j + 1, i) - w0 - gp_uy(a, e, k + 1, j, i) + v0 : 0.0;
-    if (ip) wy[c] = kp ? gp_ux(a, e, k + 1, j, i) - u0 - gp_uz(a, e, k, j, i + 1) + w0 : 0.0;
-    if (jp) {
-        if (ip) {
-            double w = gp_uy(a, e, k, j, i + 1) - v0 - gp_ux(a, e, k, j + 1, i) + u0;
-            if (fparam > 0.0) w = w + fparam;
-            wz[c] = w;
-        } else wz[c] = 0.0;
-    }
-    double acc = 0.0;
-    if (i > 0) { double q = gp_ux(a, e, k, j, i - 1); acc = acc + cx * (u0 * u0 + q * q); }
-    if (j > 0) { double q = gp_uy(a, e, k, j - 1, i); acc = acc + cy * (v0 * v0 + q * q); }
-    if (k > 0) { double q = gp_uz(a, e, k - 1, j, i); acc = acc + cz * (w0 * w0 + q * q); }
     ke[c] = acc;
 }
 
@@ -387,26 +302,6 @@ extern "C" int ny_diag_post(ny_ctx* ctx, const double* ux, const double* uy, con
     k_diag_post<<<g.grid, g.block, 0, ny_stream(stream)>>>(ux, uy, uz, Ux, Uy, Uz, wx, wy, wz, ke, idx2, idy2, idz2,
                                                            (0.5 * idx2) * 0.5, (0.5 * idy2) * 0.5, (0.5 * idz2) * 0.5,
                                                            fparam, make_ext(e), maxbits);
-    NY_CHECK_LAUNCH(ctx);
-    return NY_OK;
-}
-
-// internal: the launch behind ny_mg_project_post (ny_mg.cu owns the multigrid arrays)
-int ny_launch_gradp_post(ny_ctx* ctx, const double* xmg, long long msj, long long msk, long long m0, double scale,
-                         const double* ux, const double* uy, const double* uz, double* p, double* uxo, double* uyo, double* uzo,
-                         double* Ux, double* Uy, double* Uz, double* wx, double* wy, double* wz, double* ke,
-                         double idx2, double idy2, double idz2, double fparam, ny_ext e, cudaStream_t st)
-{
-    ny_grid3 g = ny_cells_launch(e.nz, e.ny, e.nx);
-    ny_prof_scope ps(ctx, NY_PROF_GRADP_POST, st);
-    NY_REQUIRE(ctx->scratch_doubles >= 32768 + NY_MAX_SLOTS, "scratch too small");
-    unsigned long long* maxbits = reinterpret_cast<unsigned long long*>(ctx->d_scratch + 32768);
-    NY_CUDA(cudaMemsetAsync(maxbits, 0, NY_MAX_SLOTS * sizeof(unsigned long long), st));
-    GpIn a;
-    a.x = xmg; a.msj = msj; a.msk = msk; a.m0 = m0; a.ux = ux; a.uy = uy; a.uz = uz; a.scale = scale;
-    k_gradp_post<<<g.grid, g.block, 0, st>>>(a, p, uxo, uyo, uzo, Ux, Uy, Uz, wx, wy, wz, ke, idx2, idy2, idz2,
-                                             (0.5 * idx2) * 0.5, (0.5 * idy2) * 0.5, (0.5 * idz2) * 0.5, fparam,
-                                             make_ext(e), maxbits);
     NY_CHECK_LAUNCH(ctx);
     return NY_OK;
 }

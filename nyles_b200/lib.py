@@ -101,7 +101,6 @@ _PROTOS = {
     "ny_mg_solve_directly": ([_P, _P, _P, ny_ext, C.POINTER(_I * 3), _D, C.POINTER(ny_mg_stats), _P], _I),
     "ny_mg_project": ([_P] + [_P] * 5 + [_D, _D, _D, ny_ext, C.POINTER(_I * 3), _D, C.POINTER(ny_mg_stats), _P], _I),
     "ny_diag_post": ([_P] + [_P] * 10 + [_D, _D, _D, _D, ny_ext, _P], _I),
-    "ny_mg_project_post": ([_P] + [_P] * 15 + [_D, _D, _D, _D, ny_ext, C.POINTER(_I * 3), _D, C.POINTER(ny_mg_stats), _P], _I),
     "ny_mg_op": ([_P, _I, _I, _P], _I),
     "ny_diag_post_max_speed2": ([_P, C.POINTER(_D), _P], _I),
     "ny_debug_weno5": ([_P, _P, _P, _LL, _P], _I),
@@ -178,7 +177,7 @@ def launch_count_reset():
         load().ny_launch_count_reset(h)
 
 
-NY_PROF_NTAGS = 19
+NY_PROF_NTAGS = 18
 
 
 def prof_start(mask=(1 << NY_PROF_NTAGS) - 1, device=None):

@@ -103,21 +103,6 @@ class MG(object):
                                        lib.ext(t), C.byref(self.lo), self.dx ** 2, C.byref(self._stats), lib.stream()))
         self._record()
 
-    def project_post(self, state, grid, uo, fparameter):
-        """project() and the diagnostics that follow it in diagnose_var (U, vorticity, kinetic energy, max|U|^2) with
-        the two passes over u merged (ny_mg_project_post).  The projected velocity lands in the three tensors `uo`;
-        the caller swaps them with state.u.  Closed single-rank domains only (no halo refresh in between)."""
-        u, U, w = state.u, state.U, state.vor
-        t = state.p.tensor
-        lib.check(self.L.ny_mg_project_post(
-            self.mg, lib.ptr(u["i"].tensor), lib.ptr(u["j"].tensor), lib.ptr(u["k"].tensor),
-            lib.ptr(uo[0]), lib.ptr(uo[1]), lib.ptr(uo[2]), lib.ptr(state.div.tensor), lib.ptr(t),
-            lib.ptr(U["i"].tensor), lib.ptr(U["j"].tensor), lib.ptr(U["k"].tensor),
-            lib.ptr(w["i"].tensor), lib.ptr(w["j"].tensor), lib.ptr(w["k"].tensor), lib.ptr(state.ke.tensor),
-            grid.idx2, grid.idy2, grid.idz2, float(fparameter), lib.ext(t), C.byref(self.lo), self.dx ** 2,
-            C.byref(self._stats), lib.stream()))
-        self._record()
-
     def solve(self, x, b, fill_halo=False):
         """Full-array interface: b and x have the padded multigrid shape (mgfordriver.py:101-106).
         fill_halo: fill the periodic / slab halos of b (and of the warm-start x) first, as

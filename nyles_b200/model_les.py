@@ -8,8 +8,6 @@ All fields are CUDA tensors in one canonical layout; the operator modules call l
 """
 import pickle
 
-import torch
-
 from . import variables as var
 from . import tracer
 from . import timescheme as ts
@@ -71,8 +69,6 @@ class LES(object):
         self.mg.preallocate_for_nyles(grid.dx, param["neighbours"], self.halo)
         self.stats = []
         self._umax_key = None
-        self._u_spare = None                  # three spare velocity arrays of the merged projection + diagnostics pass
-        self.merge_projection = True
 
     def cached_max_speed2(self):
         """max(U^2+V^2+W^2) left on the device by the last fused diagnose_var, or None if state.U has been
@@ -96,18 +92,6 @@ class LES(object):
         if not self.euler:                    # model_les_euler.py:98-99 has these two fills commented out
             self.halo.fill(state.b)
             self.halo.fill(state.u)
-        if self.fused and self.nonlinear and not self.neighbours and self.merge_projection:
-            # a closed box on one rank has no halo to refresh between "u -= grad p" and the diagnostics: one pass
-            # writes p, the projected u (into spare arrays, swapped in below), U, vorticity, kinetic energy, max|U|^2
-            if self._u_spare is None:
-                self._u_spare = [torch.empty_like(state.u[d].tensor) for d in "ijk"]
-            self.mg.project_post(state, self.grid, self._u_spare, self.fparameter)
-            for n, d in enumerate("ijk"):
-                state.u[d].tensor, self._u_spare[n] = self._u_spare[n], state.u[d].tensor
-            U = state.U
-            lib.u_epoch += 1
-            self._umax_key = (state, lib.u_epoch, _versions(U), tuple(U[d].tensor.data_ptr() for d in "ijk"))
-            return
         if self.fused:
             # same statements as below in three launches around the solve plus one for the diagnostics
             self.mg.project(state, self.grid)

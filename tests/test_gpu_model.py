@@ -219,37 +219,47 @@ def test_views_survive_the_buffer_rotation_and_passive_tracers_follow():
     assert float(st.u["i"].tensor.abs().max()) > 0
 
 
-@pytest.mark.parametrize("shape", [(32, 16, 16), (16, 64, 32)])
-def test_merged_projection_and_diagnostics_pass_is_bit_identical(shape):
-    """Closed box, one rank: diagnose_var writes p, the projected u, U, vorticity, kinetic energy and max|U|^2 in ONE
-    pass after the solve (ny_mg_project_post) instead of two (ny_mg_project + ny_diag_post).  Same statements,
-    same bits -- every field, dt and V-cycle count over a few steps."""
-    nz, ny_, nx = shape
-    kw = dict(nx=nx, ny=ny_, nz=nz, geometry="closed", Lx=nx / 8.0, Ly=ny_ / 8.0, Lz=nz / 8.0, cfl=0.8, dt_max=0.05)
-    runs = []
-    for merged in (True, False):
-        ny = make_nyles(kw)
-        ny.model.merge_projection = merged
-        rng = np.random.default_rng(11)
-        st = ny.model.state
-        st.b.view("i")[:] = np.tanh(rng.standard_normal((nz, ny_, nx)))
-        for d in "ijk":
-            st.u[d].view("i")[:] = 0.02 * rng.standard_normal((nz, ny_, nx))
-        ny.model.diagnose_var(st)
-        t, log = 0.0, []
-        for n in range(4):
-            dt = ny.compute_dt()
-            ny.model.forward(t, dt)
-            t += dt
-            log.append((dt, ny.model.mg.stats["nite"]))
-        fields = {s: getattr(st, s).tensor.clone() for s in SCALARS}
-        for v in VECTORS:
-            for d in "ijk":
-                fields[v + d] = getattr(st, v)[d].tensor.clone()
-        runs.append((log, fields))
-    assert runs[0][0] == runs[1][0]
-    for name in runs[0][1]:
-        assert torch.equal(runs[0][1][name], runs[1][1][name]), name
+@pytest.mark.parametrize("orders", [(5, 5), (3, 3), (1, 1)])
+def test_linear_upwind_model_vs_oracle(orders, monkeypatch):
+    """nyles_b200.LINEAR_UPWIND: the whole LES step with the reference's linear upwind branch (what Nyles does once
+    `linear` is set in fortran_upwind.f90:31 / fortran_vortex_force.f90:28,108) at orderA / orderVF, against the oracle
+    with the same switch: dt to 1e-12, fields to 1e-10 over a few steps, identical V-cycle counts."""
+    import nyles_b200
+    monkeypatch.setattr(nyles_b200, "LINEAR_UPWIND", True)
+    oa, ovf = orders
+    kw = dict(nx=32, ny=16, nz=16, geometry="closed", Lx=4.0, Ly=2.0, Lz=2.0, cfl=0.8, dt_max=0.05)
+    o = M.LES(M.make_param(orderA=oa, orderVF=ovf, **kw), linear_upwind=True)
+    from nyles_b200 import parameters, nyles
+    parameters.InextensibleDict.unfreeze()
+    up = parameters.UserParameters()
+    up.model["geometry"] = "closed"
+    up.model["Lx"], up.model["Ly"], up.model["Lz"] = kw["Lx"], kw["Ly"], kw["Lz"]
+    up.discretization["global_nx"], up.discretization["global_ny"], up.discretization["global_nz"] = 32, 16, 16
+    up.discretization["orderA"], up.discretization["orderVF"] = oa, ovf
+    up.time["cfl"], up.time["dt_max"] = kw["cfl"], kw["dt_max"]
+    up.IO["datadir"] = ""
+    ny = nyles.Nyles(up)
+    assert ny.model.tracer.linear and not ny.model.fused
+    rng = np.random.default_rng(8)
+    ic = np.tanh((o.grid.x_b - 2.0 + 0.1 * rng.standard_normal(o.grid.x_b.shape)) / (2 * o.grid.dx))
+    o.state.b.view("i")[:] = ic
+    ny.model.state.b.view("i")[:] = ic
+    o.diagnose_var(o.state)
+    ny.model.diagnose_var(ny.model.state)
+    t = 0.0
+    for n in range(5):
+        dt = o.compute_dt()
+        assert abs(ny.compute_dt() - dt) <= 1e-12 * dt
+        nlog, before = len(o.mg_log), ny.model.mg.nvcycles
+        o.forward(t, dt)
+        ny.model.forward(t, dt)
+        assert ny.model.mg.nvcycles - before == sum(m[0] for m in o.mg_log[nlog:])
+        t += dt
+    st = ny.model.state
+    assert relerr(st.b.tensor.cpu().numpy(), o.state.b.data) <= 1e-10
+    for d in "ijk":
+        assert relerr(st.u[d].tensor.cpu().numpy(), o.state.u[d].data) <= 1e-10
+    assert float(st.u["i"].tensor.abs().max()) > 0
 
 
 def test_step_host_honours_edited_host_buffers():

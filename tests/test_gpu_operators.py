@@ -513,3 +513,40 @@ def test_weno3_primitive_against_oracle():
     out = torch.empty(n, dtype=torch.float64, device="cuda")
     lib.check(L.ny_debug_weno3(lib.context(), lib.ptr(qd), lib.ptr(out), n, lib.stream()))
     assert np.array_equal(out.cpu().numpy(), ref)
+
+
+# ---------------------------------------------------------------- the linear (non-WENO) upwind branch
+@pytest.mark.parametrize("shape", SHAPES + [(9, 70, 34)])
+@pytest.mark.parametrize("order", [1, 2, 3, 4, 5])
+def test_linear_upwind_branch(K, L, shape, order):
+    """fortran_upwind.f90:33-64 with core/interpolate_tracer.f90 (dormant in the shipped reference, linear=.false.):
+    ny_upwind_linear against the oracle over the three directions as tracer.py:44-72 drives them, bit-exact."""
+    trac, Ux, Uy, Uz = rand_fields(shape, 4, 60 + order)
+    ref = np.full_like(trac, 3.0)
+    for n, ax in enumerate("ijk"):
+        dv = views(ref)[ax]
+        if ax == "i":
+            dv[...] = 0.0
+        K.upwind_linear(views(trac)[ax], views([Ux, Uy, Uz][n])[ax], dv, order)
+    g = [dev(a) for a in (trac, Ux, Uy, Uz)]
+    out = torch.full(shape, 3.0, dtype=torch.float64, device="cuda")
+    L.check(L.load().ny_upwind_linear(L.context(), *[L.ptr(t) for t in g], L.ptr(out), order, L.ext(out), L.stream()))
+    assert np.array_equal(ref, host(out))
+
+
+@pytest.mark.parametrize("shape", SHAPES + [(9, 70, 34)])
+@pytest.mark.parametrize("order", [1, 2, 3, 4, 5])
+def test_linear_vortex_force_branch(K, L, shape, order):
+    """fortran_vortex_force.f90:39-64,118-143 with core/interpolate.f90: ny_vortex_force_linear against the oracle
+    driven through the three passes of vortex_force.py:69-81, bit-exact (even orders omit the velocity, as the
+    Fortran does)."""
+    U, w, du = (rand_fields(shape, 3, 70 + order + n) for n in range(3))
+    ref = [a.copy() for a in du]
+    comp = dict(zip("ijk", range(3)))
+    for k, j, i in ["ikj", "jik", "kji"]:
+        K.vortex_force_direc(flip(U[comp[k]], j), flip(w[comp[j]], j), flip(ref[comp[i]], j), order, linear=True)
+        K.vortex_force_flip(flip(U[comp[i]], j), flip(w[comp[j]], j), flip(ref[comp[k]], j), order, linear=True)
+    gU, gw, gdu = [dev(a) for a in U], [dev(a) for a in w], [dev(a) for a in du]
+    L.check(L.load().ny_vortex_force_linear(L.context(), *[L.ptr(t) for t in gU + gw + gdu], order, L.ext(gdu[0]), L.stream()))
+    for a, t in zip(ref, gdu):
+        assert np.array_equal(a, host(t))
