@@ -263,9 +263,14 @@ static void p2p_release(ny_comm* c)
 
 // Collective: (re)allocate the receive slots for faces of up to need_bytes per direction and map the
 // neighbours' buffers.  Every rank calls it at the same point with the same size (slabs are equal).
-static int p2p_setup(ny_comm* c, size_t need_bytes, int below, int above)
+static int p2p_setup(ny_comm* c, size_t need_bytes)
 {
     ny_p2p& p = c->p2p;
+    // Always the two RING neighbours, whether or not the current geometry wraps in z: which exchanges have a partner
+    // below rank 0 / above rank P-1 changes with the topology of the model that is running, and a re-mapping decided
+    // from that would be entered by the edge ranks only -- a collective that the middle ranks never join (found at
+    // 8 ranks: closed -> perio_xyz in one process hung ranks 0 and 7 in the all-reduce below).
+    const int below = (c->rank + c->nranks - 1) % c->nranks, above = (c->rank + 1) % c->nranks;
     NY_CUDA(cudaDeviceSynchronize());
     {   // nobody may still be using the old mapping
         double* z = c->d_red;
@@ -331,12 +336,18 @@ static int p2p_exchange(ny_comm* c, double* const* arrays, const size_t* plane, 
     if (p.state < 0 || nf > 8) return NY_OK;
     size_t bytes = 0;
     for (int f = 0; f < nf; f++) bytes += (size_t)nh * plane[f] * sizeof(double);
-    if (p.state == 0 || bytes > p.slot_bytes || p.peer_rank[0] != below || p.peer_rank[1] != above) {
+    // (re)allocation is decided from values that are identical on every rank: the state and the face size
+    if (p.state == 0 || bytes > p.slot_bytes) {
         // room for four such faces: the first exchange of a run is a single field, vectors and the
         // multigrid's padded planes follow
-        int r = p2p_setup(c, p.state == 0 ? 4 * bytes : bytes, below, above);
+        int r = p2p_setup(c, p.state == 0 ? 4 * bytes : bytes);
         if (r != NY_OK) return r;
         if (p.state != 1) return NY_OK;
+    }
+    if ((below >= 0 && below != p.peer_rank[0]) || (above >= 0 && above != p.peer_rank[1])) {
+        ny_set_error("p2p_exchange: neighbours (%d, %d) are not the ring neighbours (%d, %d) of rank %d", below, above,
+                     p.peer_rank[0], p.peer_rank[1], c->rank);
+        return NY_ERR_ARG;
     }
     const unsigned long long seq = ++p.seq;
     const int slot = (int)(seq % NY_P2P_SLOTS);
