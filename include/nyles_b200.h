@@ -247,7 +247,8 @@ int  ny_mg_create_slab(ny_ctx*, ny_comm* comm, int nx, int ny, int nz_global, in
 /* Tuning defaults.  The four setters below change process-wide DEFAULTS that a multigrid copies when it is created
  * (ny_mg_create / ny_mg_create_slab); an existing multigrid keeps the values it was born with.
  * slab multigrids created afterwards gather every level with at most `cells` global cells
- * (default 64^3); a level whose slab is thinner than 4 planes is gathered in any case */
+ * (default 2 200 000: 128^3 and below; the finest level always stays distributed); a level whose slab is thinner
+ * than 4 planes is gathered in any case */
 void ny_mg_set_gather_cells(long long cells);
 /* slab levels with at least `cells` local cells compute the planes next to their slab neighbours first and
  * exchange them on a second stream while the rest of the slab is computed (default: never -- the peer-memory

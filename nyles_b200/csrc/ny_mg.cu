@@ -33,8 +33,14 @@ namespace {
 constexpr int MAXLEV = 50;
 constexpr int NH = 3;
 constexpr int MAX_PARTIALS = 1 << 15;
-long long g_gather_cells = 262144;         // levels with at most this many cells are gathered (64^3)
+// levels with at most this many cells are gathered: 128^3 (and a little: the test is <=).  64^3 in round 1; at 8 B200
+// the two face exchanges per V-cycle of a distributed 128^3 level cost more than solving it redundantly
+// (64.6 -> 64.1 ms per 1024^3 step, profiles/r2_f_*)
+long long g_gather_cells = 2200000;
 long long g_tail_cells = 4096;            // closed boxes: levels with at most this many cells form the one-launch tail of the V-cycle
+// levels with fewer cells than this run one kernel per operator instead of the fused plane-marching legs, whose
+// pipeline (6 planes of fill per chunk, ~1.4 us per plane) is latency bound on small levels
+long long g_leg_min_cells = 0;
 long long g_split_tiles = 148;            // levels with at least this many 58 x 24 tiles launch wall-free tiles separately
 // slab levels with at least this many local cells compute the planes next to their neighbours first and overlap
 // the exchange with the rest.  Off by default: with the peer-memory exchange a 1024^2 x 3 face takes 60 us, less
@@ -81,7 +87,7 @@ struct ny_mg {
     int glev;                              // first gathered level (0-based); 0 on one rank
     // tuning, fixed when the multigrid is created (copied from the process-wide defaults that the ny_mg_set_* calls
     // and the NY_MG_* environment variables set; a setter never changes an existing multigrid)
-    long long tail_cells, split_tiles_min, overlap_cells;
+    long long tail_cells, split_tiles_min, overlap_cells, leg_min_cells;
     int below, above;                      // slab neighbours (-1: none)
     double tol, omega;
     Level lev[MAXLEV];
@@ -1243,6 +1249,7 @@ bool leg_ok(const ny_mg* mg, int lev)
     const Level& L = mg->lev[lev - 1];
     if (!mg->maps[lev - 1].ok || !mg->maps[lev].ok) return false;
     if (L.nx < 4 || L.ny < 4 || L.nz - 2 * NH < 4 || ((L.nz - 2 * NH) & 1)) return false;
+    if ((long long)L.nx * L.ny * (L.nz - 2 * NH) < mg->leg_min_cells) return false;
     const bool walls_only = !mg->xper && !mg->yper && !L.zlo && !L.zhi;
     return lev > 1 || walls_only || mg->halo_ok;
 }
@@ -1597,11 +1604,14 @@ int create(ny_ctx* ctx, ny_comm* comm, int nx, int ny, int nz_global, int topolo
         if (e && *e) g_tail_cells = atoll(e);
         e = getenv("NY_MG_GATHER_CELLS");
         if (e && *e) g_gather_cells = atoll(e);
+        e = getenv("NY_MG_LEG_MIN_CELLS");
+        if (e && *e) g_leg_min_cells = atoll(e);
     }
     ny_mg* mg = new ny_mg();
     memset(mg, 0, sizeof(ny_mg));
     mg->ctx = ctx; mg->comm = P > 1 ? comm : nullptr; mg->nranks = P; mg->rank = rank;
     mg->tail_cells = g_tail_cells; mg->split_tiles_min = g_split_tiles; mg->overlap_cells = g_overlap_cells;
+    mg->leg_min_cells = g_leg_min_cells;
     mg->nh = NH; mg->maxite = 20; mg->tol = 1e-6; mg->omega = 0.9;          // mg_types.f90:15-26
     mg->topology = topology;
     mg->xper = topology == NY_TOPO_XPERIO || topology == NY_TOPO_XYPERIO || topology == NY_TOPO_XYZPERIO;
@@ -1628,11 +1638,12 @@ int create(ny_ctx* ctx, ny_comm* comm, int nx, int ny, int nz_global, int topolo
     }
     mg->nlevels = i + 1;
     // slabs: a level stays distributed while its slab is at least 4 planes thick and the level has
-    // more than 64^3 cells; from the first level that is not, everything is gathered
+    // more than g_gather_cells cells (the finest level is distributed whatever its size); from the first level that
+    // is not, everything is gathered
     mg->glev = 0;
     if (P > 1) {
         int l = 0;
-        while (l < mg->nlevels && gz[l] % P == 0 && gz[l] / P >= 4 && (long long)gx[l] * gy[l] * gz[l] > g_gather_cells) l++;
+        while (l < mg->nlevels && gz[l] % P == 0 && gz[l] / P >= 4 && (l == 0 || (long long)gx[l] * gy[l] * gz[l] > g_gather_cells)) l++;
         mg->glev = l;
         if (l == 0) {
             ny_set_error("ny_mg_create: the finest level (%dx%dx%d on %d slabs) is too small to be distributed",

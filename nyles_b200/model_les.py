@@ -90,8 +90,8 @@ class LES(object):
     @timing
     def diagnose_var(self, state):
         if not self.euler:                    # model_les_euler.py:98-99 has these two fills commented out
-            self.halo.fill(state.b)
-            self.halo.fill(state.u)
+            # model_les.py:105-106: fill(b), fill(u) -- one exchange for the four arrays
+            self.halo.fillarrays([state.b.tensor] + [state.u[d].tensor for d in "ijk"])
         if self.fused:
             # same statements as below in three launches around the solve plus one for the diagnostics
             self.mg.project(state, self.grid)

@@ -1,8 +1,10 @@
 #!/bin/bash
 mkdir -p gpurun_out
 make -s -j5 -C nyles_b200/csrc
-for b in "4,2" "8,2" "8,4" "4,4" "16,2" "2,8"; do
-  NY_GP_BLOCK=$b timeout 200 python bench.py --steps 6 --warmup 3 --no-cpu --e2e-steps 1 > gpurun_out/tmp_gp.json 2>/dev/null
-  echo "block 32,$b: $(python -c "
-import json; d=json.load(open('gpurun_out/tmp_gp.json')); s=d['roofline_step']['kernel_time_share']; print('%.2f ms/step, gradp_vorticity_ke %.2f ms/step' % (d['ms_per_step'], s.get('gradp_vorticity_ke',0)*d['ms_per_step']))")"
+for v in 0 200000 3000000 20000000; do
+  for wl in lock tgv256; do
+    NY_MG_LEG_MIN_CELLS=$v timeout 200 python bench.py --workload $wl --steps 20 --warmup 3 --no-cpu --e2e-steps 1 > gpurun_out/tmp_leg.json 2>/dev/null
+    echo "leg_min_cells $v $wl: $(python -c "
+import json; d=json.load(open('gpurun_out/tmp_leg.json')); s=d['roofline_step']['kernel_time_share']; print('%.3f ms/step' % d['ms_per_step'], {k: round(v*d['ms_per_step'],2) for k,v in list(s.items())[:6]})")"
+  done
 done

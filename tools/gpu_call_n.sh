@@ -10,7 +10,7 @@ grep -E "dist_check|FAIL" gpurun_out/r2f_dist_check_n$N.log | head -5
 timeout 900 $TR bench.py --gpus $N --steps 10 --warmup 3 --e2e-steps 3 > gpurun_out/r2f_bench_n$N.json 2> gpurun_out/r2f_bench_n$N.err
 python tools/show_bench.py gpurun_out/r2f_bench_n$N.json | head -15
 grep -o '"parity_check": "[a-zA-Z]*"' gpurun_out/r2f_bench_n$N.json; grep -o '"nvlink": {[^}]*}' gpurun_out/r2f_bench_n$N.json
-if [ "$N" = "8" ]; then
+if [ "$N" = "8" ] && [ -n "$PLUME" ]; then
   timeout 900 $TR bench.py --gpus $N --workload plume --steps 8 --warmup 3 --e2e-steps 2 --no-selfcheck > gpurun_out/r2f_bench_plume_n$N.json 2> gpurun_out/r2f_bench_plume_n$N.err
   python tools/show_bench.py gpurun_out/r2f_bench_plume_n$N.json | head -15; tail -2 gpurun_out/r2f_bench_plume_n$N.err
   NY_MG_GATHER_CELLS=2200000 timeout 900 $TR bench.py --gpus $N --steps 10 --warmup 3 --e2e-steps 1 --no-selfcheck > gpurun_out/r2f_bench_n${N}_gather128.json 2> gpurun_out/r2f_bench_n${N}_gather128.err
