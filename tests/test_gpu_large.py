@@ -41,6 +41,9 @@ def make_nyles(kw):
     up.discretization["global_nx"], up.discretization["global_ny"], up.discretization["global_nz"] = \
         kw["nx"], kw["ny"], kw["nz"]
     up.time["cfl"], up.time["dt_max"] = kw["cfl"], kw["dt_max"]
+    for k in ("rotating", "coriolis", "forced"):
+        if k in kw:
+            up.physics[k] = kw[k]
     up.IO["datadir"] = ""
     return nyles.Nyles(up)
 
@@ -86,16 +89,40 @@ def case_rt(n):
     return kw, ic
 
 
+def case_plume(n):
+    """configs[3] scaled down: experiments/forced_convection/forced_plume.py (closed, LES, rotating f = 1, Gaussian
+    column heat source, linear stratification) on an n x n x n/2 box; the forcing object offers device_tendencies, so
+    the CUDA side runs its fused RHS + time-scheme launches with the source added in-kernel."""
+    nx, nz = n, n // 2
+    kw = dict(nx=nx, ny=nx, nz=nz, geometry="closed", Lx=16.0, Ly=16.0, Lz=8.0, modelname="LES", cfl=0.8, dt_max=0.8,
+              rotating=True, coriolis=1.0, forced=True)
+
+    def ic(grid):
+        rng = np.random.default_rng(4321)
+        shape = (nz, nx, nx)
+        z = grid.z_b_1D[:, None, None] / kw["Lz"]
+        out = {"b": np.broadcast_to(0.1 * (z - 0.5), shape).copy()}
+        dx = kw["Lx"] / nx
+        for d in "ijk":                             # the plume starts from rest; a little noise wakes every term up
+            out["u_" + d] = 0.05 * dx * rng.standard_normal(shape)
+        return out
+    return kw, ic
+
+
 SCALARS = ("b", "p", "ke", "div")
 VECTORS = ("u", "U", "vor")
 
 
-@pytest.mark.parametrize("case", ["tgv", "rt"])
+@pytest.mark.parametrize("case", ["tgv", "rt", "plume"])
 def test_benchmark_size_against_oracle(case):
-    kw, ic = (case_tgv if case == "tgv" else case_rt)(N)
+    kw, ic = {"tgv": case_tgv, "rt": case_rt, "plume": case_plume}[case](N)
     euler = kw["modelname"] == "Euler3d"
     o = M.LES(M.make_param(**kw), flavour="strictomp")
     ny = make_nyles(kw)
+    if kw.get("forced"):
+        from golden_cases import DevicePlumeForcing, PlumeForcing
+        o.forcing = PlumeForcing(o.param, o.grid)
+        ny.model.forcing = DevicePlumeForcing(ny.param, ny.grid)
     assert np.array_equal(np.asarray(ny.grid.x_b_1D), o.grid.x_b_1D)
     fields = ic(o.grid)
     for name, a in fields.items():
