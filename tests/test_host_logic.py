@@ -182,3 +182,89 @@ def test_c_example_links_against_the_library(tmp_path):
     lib.load()
     r = build_c_example(str(tmp_path / "c_abi_example"))
     assert r.returncode == 0, r.stderr
+
+
+def test_sub_views_are_bound_to_the_scalar_not_to_a_buffer():
+    """b.view('i')[k0:k1] keeps a chain of indices and re-applies it to the Scalar's current tensor: the fused step
+    rotates buffers, and views held by experiment scripts must keep showing the field (CPU storage, no kernels)."""
+    import torch
+    from nyles_b200 import variables as var
+    param = dict(nx=8, ny=6, nz=4, nh=3, neighbours={}, device="cpu")
+    s = var.Scalar(param, "buoyancy", "b", "L.T^-2", True)
+    s.tensor[:] = torch.arange(s.tensor.numel(), dtype=torch.float64).reshape(s.tensor.shape)
+    sub = s.view("i")[1:3][:, 2:5]
+    subj = s.view("j")[2:6]
+    first = np.asarray(sub).copy()
+    assert np.array_equal(first, s.tensor.numpy()[1:3][:, 2:5])
+    s.tensor = s.tensor + 1000.0                          # what LES.rhs_step does: another buffer becomes the field
+    assert np.array_equal(np.asarray(sub), first + 1000.0)
+    assert np.array_equal(np.asarray(subj), s.tensor.permute(2, 0, 1).numpy()[2:6])
+    sub[:] = -1.0                                          # writes land in the live field
+    assert float(s.tensor[1:3, 2:5].max()) == -1.0 and float(s.tensor[0].min()) >= 1000.0
+    assert isinstance(s.view("i")[0, 0, 0], float)
+
+
+def test_bench_workloads_and_cpu_samples():
+    """bench.py's workload table: the five BASELINE configs map to grids / models as SURVEY.md 8(d) lists them, the
+    CPU sample of a workload is the same set-up on a smaller box, and the forcing of the plume offers both protocols."""
+    import argparse
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    w = bench.workload("weak512", 8)
+    assert (w["nx"], w["ny"], w["nz"]) == (1024, 1024, 1024) and w["geometry"] == "closed" and w["modelname"] == "LES"
+    w = bench.workload("tgv256", 1)
+    assert w["geometry"] == "perio_xyz" and w["modelname"] == "Euler3d" and abs(w["dt_max"] - 0.05) < 1e-15
+    w = bench.workload("plume", 8)
+    assert (w["nx"], w["ny"], w["nz"]) == (1024, 1024, 512) and w["rotating"] and w["forced"] and w["scaling"] == "strong"
+    assert abs(w["nx"] * w["dx"] - 16.0) < 1e-12 and abs(w["nz"] * w["dx"] - 8.0) < 1e-12
+    w = bench.workload("rt512strong", 2)
+    assert (w["nx"], w["ny"], w["nz"]) == (512, 512, 512) and w["scaling"] == "strong"
+    assert bench.workload("lock", 1)["nx"] == 128
+    for wl, sample in (("weak512", "rayleigh-taylor 256^3"), ("tgv256", "taylor-green vortex 128^3"),
+                       ("plume", "turbulent plume 256x256x128"), ("lock", "lock-exchange")):
+        a = argparse.Namespace(cpu_sample="auto", workload=wl, gpus=1)
+        s, same = bench.cpu_sample(a)
+        assert s["name"].startswith(sample), (wl, s["name"])
+        assert same == (wl == "lock")
+    s, same = bench.cpu_sample(argparse.Namespace(cpu_sample="same", workload="weak512", gpus=1))
+    assert same and s["nx"] == 512
+    w = bench.workload("plume256", 1)
+    x = (np.arange(w["nx"]) + 0.5) * w["dx"]
+    z = (np.arange(w["nz"]) + 0.5) * w["dx"]
+    f = bench.PlumeForcing(w, x, x, z)
+    assert f.Q.shape == (w["nz"], w["ny"], w["nx"]) and f.Q.max() <= 0.1 and f.Q.min() >= 0.0
+    assert f.device_tendencies(None, 0.0)["b"] is f.Q
+    b, u, v = bench.initial_condition(w, x, x, z, 0)
+    assert u is None and abs(b[0, 0, 0] - 0.1 * (z[0] / 8.0 - 0.5)) < 1e-15
+    assert bench.bytes_per_cell_step(w, 8.0) == 1080.0 + 199.0 * 8.0
+
+
+def test_ncu_facts_are_stamped_with_the_kernel_sources():
+    """profiles/ncu_traffic.json carries a hash of nyles_b200/csrc; bench.py only quotes DRAM traffic and fp64
+    instruction counts taken from the sources the library was built from."""
+    import importlib.util
+    import json
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from ncu_traffic import source_stamp
+    stamp = source_stamp()
+    assert len(stamp) == 16 and stamp == source_stamp()
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    d = json.load(open(path))
+    assert {"stamp", "families", "fp64"} <= set(d)
+    spec = importlib.util.spec_from_file_location("bench_mod2", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    facts = bench.ncu_facts()
+    assert facts["stale"] == (facts.get("stamp") != stamp)
+
+
+def test_selfcheck_cases_cover_the_three_topologies():
+    from nyles_b200 import selfcheck
+    for world in (2, 4, 8):
+        cs = selfcheck.cases(world)
+        assert [c["geometry"] for c in cs] == ["closed", "perio_xyz", "perio_xy"]
+        assert all(c["n"] == (64, 64, 64 * world) for c in cs)
+        assert cs[1]["modelname"] == "Euler3d" and cs[2].get("rotating")
