@@ -244,7 +244,7 @@ int  ny_mg_create(ny_ctx*, int nx, int ny, int nz, int topology, ny_mg** out);
  * (z halos filled from the neighbours through NCCL); small levels are gathered and solved
  * redundantly (mg_setup.f90:275-293).  Collective: every rank must make the same calls. */
 int  ny_mg_create_slab(ny_ctx*, ny_comm* comm, int nx, int ny, int nz_global, int topology, ny_mg** out);
-/* Tuning defaults.  The four setters below change process-wide DEFAULTS that a multigrid copies when it is created
+/* Tuning defaults.  The five setters below change process-wide DEFAULTS that a multigrid copies when it is created
  * (ny_mg_create / ny_mg_create_slab); an existing multigrid keeps the values it was born with.
  * slab multigrids created afterwards gather every level with at most `cells` global cells
  * (default 2 200 000: 128^3 and below; the finest level always stays distributed); a level whose slab is thinner
@@ -257,9 +257,14 @@ void ny_mg_set_overlap_cells(long long cells);
 /* fused legs: levels whose plane holds at least `tiles` 58 x 24 tiles launch the tiles that keep clear of the
  * x / y walls as a separate, wall-free kernel instance (default 148 = one per SM; tests lower it) */
 void ny_mg_set_split_tiles(long long tiles);
-/* closed boxes: the levels with at most `cells` cells (default 4096 = 16^3) form the tail of the V-cycle that
- * one single-CTA launch runs from the first smoothing down to the coarsest level and back (0: off) */
+/* the levels with at most `cells` cells (default 2048) form the tail of the V-cycle that one single-CTA launch
+ * runs from the first smoothing down to the coarsest level and back (0: off) */
 void ny_mg_set_tail_cells(long long cells);
+/* ... and the replicated levels above those with at most `cells` cells (default 300 000: 64^3 and below, or all of
+ * a 128 x 32 x 32 grid) join that launch as its "wide" levels: a cooperative launch of one CTA per SM runs them with a
+ * grid barrier between the operators, CTA 0 runs the single-CTA levels (0: no wide levels).  Same arithmetic, same
+ * results as the fused legs and the per-operator kernels. */
+void ny_mg_set_wide_cells(long long cells);
 void ny_mg_destroy(ny_mg*);
 int  ny_mg_nlevels(ny_mg*);
 /* 1 if the mask is the default box, so that the fused analytic-coefficient kernels are in use */

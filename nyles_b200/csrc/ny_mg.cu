@@ -37,7 +37,12 @@ constexpr int MAX_PARTIALS = 1 << 15;
 // the two face exchanges per V-cycle of a distributed 128^3 level cost more than solving it redundantly
 // (64.6 -> 64.1 ms per 1024^3 step, profiles/r2_f_*)
 long long g_gather_cells = 2200000;
-long long g_tail_cells = 4096;            // closed boxes: levels with at most this many cells form the one-launch tail of the V-cycle
+long long g_tail_cells = 2048;            // levels with at most this many cells form the one-launch tail of the V-cycle (one CTA)
+// ... and the replicated levels above them with at most this many cells join that launch as its "wide" levels, run
+// by a co-resident grid with grid barriers between the operators (0: none): 64^3 and a little.  Measured
+// (profiles/r2_l_*): 64^3 .. 16^3 levels and the whole 128 x 32 x 32 lock-exchange grid are faster wide than through
+// the fused legs, which stay with the levels from 128^3 up.
+long long g_wide_cells = 300000;
 // levels with fewer cells than this run one kernel per operator instead of the fused plane-marching legs, whose
 // pipeline (6 planes of fill per chunk, ~1.4 us per plane) is latency bound on small levels
 long long g_leg_min_cells = 0;
@@ -87,7 +92,9 @@ struct ny_mg {
     int glev;                              // first gathered level (0-based); 0 on one rank
     // tuning, fixed when the multigrid is created (copied from the process-wide defaults that the ny_mg_set_* calls
     // and the NY_MG_* environment variables set; a setter never changes an existing multigrid)
-    long long tail_cells, split_tiles_min, overlap_cells, leg_min_cells;
+    long long tail_cells, wide_cells, split_tiles_min, overlap_cells, leg_min_cells;
+    int wide_max_blocks;                   // CTAs of k_vcycle_tail that a cooperative launch can hold (0: no wide levels)
+    unsigned* d_bar;                       // grid barrier of the wide levels: arrivals, generation
     int below, above;                      // slab neighbours (-1: none)
     double tol, omega;
     Level lev[MAXLEV];
@@ -708,49 +715,117 @@ k_prolong_box(double* __restrict__ xf, const double* __restrict__ xc, Box g, Box
 
 // ---- the tail of the V-cycle in ONE launch -------------------------------------------------------
 // Levels of a few thousand cells cost ~20 us per leg as separate launches (pipeline fill, launch and
-// drain dominate) and there are a dozen of them per V-cycle.  For closed boxes (no halo fill between the
-// operators) one CTA runs the whole tail -- smooth, residual + restriction down to the coarsest level, its
-// smoothing, prolongation + smooth back up -- with a block barrier between the operators.  The arrays stay
-// in global memory (a CTA sees its own writes after __syncthreads; no read-only-path loads).  Per-cell
-// arithmetic and operation order are those of k_sweep / k_residual / k_restrict / k_prolong with the
+// drain dominate) and there are a dozen of them per V-cycle.  One launch runs the whole tail -- smooth,
+// residual + restriction down to the coarsest level, its smoothing, prolongation + smooth back up -- with a
+// barrier between the operators.  Two kinds of level:
+//   narrow (at most tail_cells cells): one CTA, __syncthreads between the operators;
+//   wide   (at most wide_cells cells): every CTA of a co-resident grid (cooperative launch, one CTA per SM),
+//          a grid barrier between the operators.  The plane-marching legs have too few tiles on such levels
+//          (a 128 x 32 plane is four tiles), so that a leg costs 25-45 us whatever the level holds; one cell per
+//          thread and ~3 us per barrier is several times faster there.
+// The wide levels are the leading ones; CTA 0 runs the narrow levels while the others wait at the barrier
+// that ends them.  The arrays stay in global memory (the barrier fences; no read-only-path loads).
+// Per-cell arithmetic and operation order are those of k_sweep / k_residual / k_restrict / k_prolong with the
 // analytic box coefficients, hence of the reference (basicoperators.f90:32-60,173-231,300-323,363-400).
-constexpr int TAIL_MAX = 8;
+constexpr int TAIL_MAX = 10;
 constexpr int TAIL_THREADS = 1024;
-struct TailLevel { double *x, *y, *b; Box g; };
-struct TailArgs { int n; double omega, cff1; TailLevel lev[TAIL_MAX]; };
+// n / d for 0 <= n < 2^31 and a divisor known on the host, as a multiplication (Granlund & Montgomery 1994, N = 32:
+// l = ceil(log2 d), m = floor(2^32 (2^l - d) / d) + 1, n / d = (mulhi(m, n) + n) >> l): the tail deals cells to threads
+// by their linear index, and a hardware-less 32-bit division per index costs more than the stencil itself
+struct FastDiv { unsigned m, l; };
+inline FastDiv fastdiv_of(int d)
+{
+    FastDiv f;
+    f.l = 0;
+    while ((1ull << f.l) < (unsigned long long)d) f.l++;
+    f.m = (unsigned)(((1ull << 32) * ((1ull << f.l) - (unsigned long long)d)) / (unsigned long long)d + 1ull);
+    return f;
+}
+__device__ __forceinline__ int fdiv(int n, const FastDiv& f)
+{
+    return (int)((__umulhi(f.m, (unsigned)n) + (unsigned)n) >> f.l);
+}
+// fx / fy: divisions by nx / ny + {0, 2, 2 NH}: the interior, the interior widened by one ring, the whole plane
+struct TailLevel { double *x, *y, *b; Box g; FastDiv fx[3], fy[3]; };
+struct TailArgs {
+    int n, nwide;
+    unsigned* bar;
+    double* norm_partial;                    // not null: sum r^2 of the first level after the cycle: one partial per CTA,
+    double *norm_out, *norm_host;            //   their sum to the device slot and to the host's pinned mailbox
+    double omega, cff1;
+    TailLevel lev[TAIL_MAX];
+};
 
-// Cells of an ni x nj x nk box dealt to the threads of the CTA in row-major order, without a division per
-// cell: (i, j, k) of the thread's first cell, then steps of TAIL_THREADS cells with carries.
-struct TailIter {
-    int i, j, k, di, dj, dk, ni, nj, left;
-    __device__ __forceinline__ TailIter(int ni_, int nj_, int nk_) : ni(ni_), nj(nj_)
-    {
-        const int t = threadIdx.x, total = ni_ * nj_ * nk_;
-        i = t % ni_; int q = t / ni_; j = q % nj_; k = q / nj_;
-        di = TAIL_THREADS % ni_; q = TAIL_THREADS / ni_; dj = q % nj_; dk = q / nj_;
-        left = t < total ? (total - t + TAIL_THREADS - 1) / TAIL_THREADS : 0;
+// Sense-reversing barrier over the CTAs of a cooperative launch: bar[0] counts arrivals, bar[1] is the generation.
+// Thread 0 arrives with an acq_rel atomic (release: what its CTA wrote before the block barrier; acquire: what the
+// CTAs that arrived earlier wrote), the last one opens the next generation with a release store, the others poll it
+// with acquire loads; the block barriers extend the ordering to the rest of the CTA.
+__device__ __forceinline__ void tail_grid_barrier(unsigned* bar)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned gen, now, prev;
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(bar + 1) : "memory");
+        asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(bar) : "memory");
+        if (prev == gridDim.x - 1) {
+            asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(bar), "r"(0u) : "memory");
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(bar + 1), "r"(gen + 1) : "memory");
+        } else {
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(now) : "l"(bar + 1) : "memory");
+            } while (now == gen);
+        }
     }
-    __device__ __forceinline__ void next()
+    __syncthreads();
+}
+
+// the threads that share an operator: index t of T, and their barrier
+struct TailTeam {
+    int t, T;
+    unsigned* bar;                           // nullptr: the threads of one CTA
+    bool on;                                 // this thread belongs to the team
+    __device__ __forceinline__ void sync() const { if (bar) tail_grid_barrier(bar); else __syncthreads(); }
+};
+
+// cnt_xy / cnt_z without branches (the tail's phases are issue bound: a thread has one or two cells per operator)
+__device__ __forceinline__ int tin_x(const Box& g, int ai) { return g.xper | (int)((unsigned)(ai - NH) < (unsigned)g.nx); }
+__device__ __forceinline__ int tin_y(const Box& g, int aj) { return g.yper | (int)((unsigned)(aj - NH) < (unsigned)g.ny); }
+__device__ __forceinline__ int tin_z(const Box& g, int ak) { return ((int)(ak >= NH) | g.zlo) & ((int)(ak < g.nz - NH) | g.zhi); }
+__device__ __forceinline__ int tail_cnt(const Box& g, int ai, int aj, int ak)
+{
+    const int inside = tin_x(g, ai) & tin_y(g, aj) & tin_z(g, ak);
+    const int n = tin_x(g, ai - 1) + tin_x(g, ai + 1) + tin_y(g, aj - 1) + tin_y(g, aj + 1) + tin_z(g, ak - 1) + tin_z(g, ak + 1);
+    return inside ? n : -100;              // cnt_xy + cnt_z wherever that sum is positive; negative elsewhere, as it is
+}
+
+// (i, j, k) of cell c of an ni x nj x nk box in row-major order; the threads of a team take cells t, t + T, ...
+struct TailCell {
+    int i, j, k;
+    __device__ __forceinline__ TailCell(int c, int ni, int nj, const FastDiv& fi, const FastDiv& fj)
     {
-        i += di; if (i >= ni) { i -= ni; j++; }
-        j += dj; if (j >= nj) { j -= nj; k++; }
-        k += dk;
-        left--;
+        const int q = fdiv(c, fi);
+        i = c - q * ni;
+        k = fdiv(q, fj);
+        j = q - k * nj;
     }
 };
 
 // one Jacobi sweep src -> dst on the interior widened by `ring` cells (fsmoother3d: ring 1, then ring 0)
-__device__ __forceinline__ void tail_sweep(const double* src, double* dst, const double* b, const Box& g,
-                                           double omega, double cff1, int ring)
+__device__ __forceinline__ void tail_sweep(const double* src, double* dst, const TailLevel& L, double omega, double cff1,
+                                           int ring, const TailTeam& tm, const double* recip)
 {
-    TailIter it(g.nx + 2 * ring, g.ny + 2 * ring, g.nz - 2 * NH + 2 * ring);
+    const Box& g = L.g;
+    const double* b = L.b;
+    const int ni = g.nx + 2 * ring, nj = g.ny + 2 * ring, total = ni * nj * (g.nz - 2 * NH + 2 * ring);
+    const FastDiv fi = L.fx[ring], fj = L.fy[ring];
 #pragma unroll 2
-    for (; it.left > 0; it.next()) {
+    for (int t = tm.t; t < total; t += tm.T) {
+        const TailCell it(t, ni, nj, fi, fj);
         const int ai = NH - ring + it.i, aj = NH - ring + it.j, ak = NH - ring + it.k;
         const long long c = (long long)ak * g.sk + (long long)aj * g.sj + ai;
         const double s = src[c - 1] + src[c + 1] + src[c - g.sj] + src[c + g.sj] + src[c - g.sk] + src[c + g.sk];
-        const int cnt = cnt_xy(g, ai, aj) + cnt_z(g, ak);
-        const double idiag = cnt > 0 ? 1.0 / (double)cnt : 0.0;
+        const int cnt = tail_cnt(g, ai, aj, ak);
+        const double idiag = cnt > 0 ? recip[cnt] : 0.0;               // 1 / cnt, correctly rounded
         dst[c] = cff1 * src[c] + omega * (s - b[c]) * idiag;
     }
 }
@@ -759,14 +834,14 @@ __device__ __forceinline__ double tail_resid(const double* x, const double* b, c
 {
     const long long c = (long long)ak * g.sk + (long long)aj * g.sj + ai;
     const double s = x[c - 1] + x[c + 1] + x[c - g.sj] + x[c + g.sj] + x[c - g.sk] + x[c + g.sk];
-    const double diag = (double)(cnt_xy(g, ai, aj) + cnt_z(g, ak));
+    const double diag = (double)tail_cnt(g, ai, aj, ak);            // interior cells only: cnt_xy + cnt_z
     return b[c] + diag * x[c] - s;
 }
 
 constexpr int TAIL_STAGE = 2048;          // doubles of staging for array sections that overlap themselves
 
 // array section dst = src with Fortran semantics (right-hand side evaluated first), Fortran indices as in
-// k_box_copy; every thread of the CTA takes part, the section is complete when the call returns
+// k_box_copy; every thread of ONE CTA takes part (narrow levels only), the section is complete when the call returns
 __device__ __forceinline__ void tail_assign_box(double* a, const Box& g, int di0, int dj0, int dk0, int si0, int sj0, int sk0,
                                                 int ni, int nj, int nk, bool staged, double* stage)
 {
@@ -792,34 +867,15 @@ __device__ __forceinline__ void tail_assign_box(double* a, const Box& g, int di0
     __syncthreads();
 }
 
-// periodic halo fill of a replicated level inside the tail: the rule of k_fill_periodic where every wrapped axis is
-// at least nh wide, the statement sequence of mod_halo.f90:235-262 (fill_sequential) on the tiny levels below that
-__device__ __forceinline__ void tail_fill(double* a, const Box& g, double* stage)
+// the statement sequence of mod_halo.f90:235-262 (fill_sequential) for the tiny periodic levels whose halo sections
+// overlap themselves (an axis narrower than the halo); one CTA, kept out of line: it is rare and large
+__device__ __noinline__ void tail_fill_sequential(double* a, int nx, int ny, int nz, long long sj, long long sk,
+                                                  int xper, int yper, int wz, double* stage)
 {
-    const bool wz = g.zlo && g.zhi;
-    if (!(g.xper || g.yper || wz)) return;
-    const int nx = g.nx, ny = g.ny, nz = g.nz, nzi = nz - 2 * NH;
-    const bool simple = (!g.xper || nx >= NH) && (!g.yper || ny >= NH) && (!wz || nzi >= NH);
-    if (simple) {
-        const int tx = nx + 2 * NH, ty = ny + 2 * NH, n = tx * ty * nz;
-        for (int t = threadIdx.x; t < n; t += TAIL_THREADS) {
-            const int ai = t % tx, q = t / tx, aj = q % ty, ak = q / ty;
-            const bool hx = ai < NH || ai >= nx + NH, hy = aj < NH || aj >= ny + NH, hz = ak < NH || ak >= nz - NH;
-            int si = ai, sjj = aj, skk = ak;
-            if (hz && wz) skk = ak < NH ? ak + nzi : ak - nzi;
-            if (hx && hy) {
-                if (g.xper && g.yper) { si = ai < NH ? ai + nx : ai - nx; sjj = aj < NH ? aj + ny : aj - ny; }
-            } else if (hx) {
-                if (g.xper) si = ai < NH ? ai + nx : ai - nx;
-            } else if (hy) {
-                if (g.yper) sjj = aj < NH ? aj + ny : aj - ny;
-            }
-            if (si != ai || sjj != aj || skk != ak)
-                a[(long long)ak * g.sk + (long long)aj * g.sj + ai] = a[(long long)skk * g.sk + (long long)sjj * g.sj + si];
-        }
-        __syncthreads();
-        return;
-    }
+    Box g;                                   // (by value: a reference into the kernel's parameters would drag them all
+    g.nx = nx; g.ny = ny; g.nz = nz; g.sj = sj; g.sk = sk;                   //  into local memory)
+    g.xper = xper; g.yper = yper; g.zlo = wz; g.zhi = wz;
+    const int nzi = nz - 2 * NH;
     const int nh = NH;
     if (g.xper) {
         const bool ov = nx < nh;
@@ -845,50 +901,105 @@ __device__ __forceinline__ void tail_fill(double* a, const Box& g, double* stage
     }
 }
 
+
+// periodic halo fill of a replicated level inside the tail: the rule of k_fill_periodic where every wrapped axis is
+// at least nh wide, the statement sequence of mod_halo.f90:235-262 (fill_sequential) on the tiny levels below that
+// (those are narrow levels: tail_first sees to it)
+__device__ __forceinline__ void tail_fill(double* a, const TailLevel& L, double* stage, const TailTeam& tm)
+{
+    const Box& g = L.g;
+    const FastDiv fx = L.fx[2], fy = L.fy[2];
+    const bool wz = g.zlo && g.zhi;
+    if (!(g.xper || g.yper || wz)) return;
+    const int nx = g.nx, ny = g.ny, nz = g.nz, nzi = nz - 2 * NH;
+    const bool simple = (!g.xper || nx >= NH) && (!g.yper || ny >= NH) && (!wz || nzi >= NH);
+    if (simple) {
+        const int tx = nx + 2 * NH, ty = ny + 2 * NH, n = tx * ty * nz;
+        for (int t = tm.t; t < n; t += tm.T) {
+            const TailCell it(t, tx, ty, fx, fy);
+            const int ai = it.i, aj = it.j, ak = it.k;
+            const bool hx = ai < NH || ai >= nx + NH, hy = aj < NH || aj >= ny + NH, hz = ak < NH || ak >= nz - NH;
+            int si = ai, sjj = aj, skk = ak;
+            if (hz && wz) skk = ak < NH ? ak + nzi : ak - nzi;
+            if (hx && hy) {
+                if (g.xper && g.yper) { si = ai < NH ? ai + nx : ai - nx; sjj = aj < NH ? aj + ny : aj - ny; }
+            } else if (hx) {
+                if (g.xper) si = ai < NH ? ai + nx : ai - nx;
+            } else if (hy) {
+                if (g.yper) sjj = aj < NH ? aj + ny : aj - ny;
+            }
+            if (si != ai || sjj != aj || skk != ak)
+                a[(long long)ak * g.sk + (long long)aj * g.sj + ai] = a[(long long)skk * g.sk + (long long)sjj * g.sj + si];
+        }
+        tm.sync();
+        return;
+    }
+    tail_fill_sequential(a, nx, ny, nz, g.sj, g.sk, g.xper, g.yper, (int)wz, stage);
+}
+
 __global__ void __launch_bounds__(TAIL_THREADS, 1)
 k_vcycle_tail(TailArgs a)
 {
     __shared__ double stage[TAIL_STAGE];
+    __shared__ double recip[8];
+    if (threadIdx.x < 8) recip[threadIdx.x] = threadIdx.x ? 1.0 / (double)threadIdx.x : 0.0;
+    __syncthreads();
     const double omega = a.omega, cff1 = a.cff1;
-    auto smooth = [&](const TailLevel& L) {
-        tail_sweep(L.x, L.y, L.b, L.g, omega, cff1, 1);
-        __syncthreads();
-        tail_sweep(L.y, L.x, L.b, L.g, omega, cff1, 0);
-        __syncthreads();
-        tail_fill(L.x, L.g, stage);                      // operators.f90:168
+    const int nwide = a.nwide;
+    // levels [0, nwide): all CTAs; levels [nwide, n): CTA 0
+    const TailTeam wide = {(int)(blockIdx.x * TAIL_THREADS + threadIdx.x), (int)(gridDim.x * TAIL_THREADS), a.bar, true};
+    const TailTeam narrow = {(int)threadIdx.x, TAIL_THREADS, nullptr, blockIdx.x == 0};
+    auto team = [&](int l) -> const TailTeam& { return l < nwide ? wide : narrow; };
+    auto smooth = [&](const TailLevel& L, const TailTeam& tm) {
+        tail_sweep(L.x, L.y, L, omega, cff1, 1, tm, recip);
+        tm.sync();
+        tail_sweep(L.y, L.x, L, omega, cff1, 0, tm, recip);
+        tm.sync();
+        tail_fill(L.x, L, stage, tm);                    // operators.f90:168
     };
     for (int l = 0; l + 1 < a.n; l++) {                 // solvers.f90:41-46
         const TailLevel& F = a.lev[l];
         const TailLevel& C = a.lev[l + 1];
-        smooth(F);
+        const TailTeam& tf = team(l);
+        const TailTeam& tc = team(l + 1);
         const Box& g = F.g;
         const Box& gc = C.g;
-        for (TailIter it(gc.nx, gc.ny, gc.nz - 2 * NH); it.left > 0; it.next()) {
-            const int ic = it.i, jc = it.j, kc = it.k;
-            const int ai = NH + 2 * ic, aj = NH + 2 * jc, ak = NH + 2 * kc;
-            double r = tail_resid(F.x, F.b, g, ai, aj, ak);                     // frestrict_centers3d order
-            r = r + tail_resid(F.x, F.b, g, ai + 1, aj, ak);
-            r = r + tail_resid(F.x, F.b, g, ai, aj + 1, ak);
-            r = r + tail_resid(F.x, F.b, g, ai + 1, aj + 1, ak);
-            r = r + tail_resid(F.x, F.b, g, ai, aj, ak + 1);
-            r = r + tail_resid(F.x, F.b, g, ai + 1, aj, ak + 1);
-            r = r + tail_resid(F.x, F.b, g, ai, aj + 1, ak + 1);
-            r = r + tail_resid(F.x, F.b, g, ai + 1, aj + 1, ak + 1);
-            C.b[(long long)(NH + kc) * gc.sk + (long long)(NH + jc) * gc.sj + (NH + ic)] = 0.5 * r;
+        if (tf.on) {
+            smooth(F, tf);
+            const int ncells = gc.nx * gc.ny * (gc.nz - 2 * NH);
+            for (int t = tf.t; t < ncells; t += tf.T) {
+                const TailCell it(t, gc.nx, gc.ny, C.fx[0], C.fy[0]);
+                const int ic = it.i, jc = it.j, kc = it.k;
+                const int ai = NH + 2 * ic, aj = NH + 2 * jc, ak = NH + 2 * kc;
+                double r = tail_resid(F.x, F.b, g, ai, aj, ak);                     // frestrict_centers3d order
+                r = r + tail_resid(F.x, F.b, g, ai + 1, aj, ak);
+                r = r + tail_resid(F.x, F.b, g, ai, aj + 1, ak);
+                r = r + tail_resid(F.x, F.b, g, ai + 1, aj + 1, ak);
+                r = r + tail_resid(F.x, F.b, g, ai, aj, ak + 1);
+                r = r + tail_resid(F.x, F.b, g, ai + 1, aj, ak + 1);
+                r = r + tail_resid(F.x, F.b, g, ai, aj + 1, ak + 1);
+                r = r + tail_resid(F.x, F.b, g, ai + 1, aj + 1, ak + 1);
+                C.b[(long long)(NH + kc) * gc.sk + (long long)(NH + jc) * gc.sj + (NH + ic)] = 0.5 * r;
+            }
+            const long long nc = gc.sk * gc.nz;
+            for (long long t = tf.t; t < nc; t += tf.T) C.x[t] = 0.0;               // operators.f90:209
+            tf.sync();
         }
-        const long long nc = gc.sk * gc.nz;
-        for (long long t = threadIdx.x; t < nc; t += TAIL_THREADS) C.x[t] = 0.0;   // operators.f90:209
-        __syncthreads();
-        tail_fill(C.b, gc, stage);                       // operators.f90:211
+        if (tc.on) tail_fill(C.b, C, stage, tc);         // operators.f90:211
     }
-    smooth(a.lev[a.n - 1]);
+    if (team(a.n - 1).on) smooth(a.lev[a.n - 1], team(a.n - 1));
     for (int l = a.n - 2; l >= 0; l--) {                // solvers.f90:51-54
         const TailLevel& F = a.lev[l];
         const TailLevel& C = a.lev[l + 1];
+        const TailTeam& tf = team(l);
         const Box& g = F.g;
         const Box& gc = C.g;
+        if (l == nwide - 1 && nwide < a.n) wide.sync();   // what CTA 0 did on the narrow levels becomes visible
+        if (!tf.on) continue;
+        const int nfine = g.nx * g.ny * (g.nz - 2 * NH);
 #pragma unroll 2
-        for (TailIter it(g.nx, g.ny, g.nz - 2 * NH); it.left > 0; it.next()) {
+        for (int t = tf.t; t < nfine; t += tf.T) {
+            const TailCell it(t, g.nx, g.ny, F.fx[0], F.fy[0]);
             const int fi = it.i, fj = it.j, fk = it.k;                              // 0-based interior fine cell
             const int aic = NH + (fi >> 1), ajc = NH + (fj >> 1), akc = NH + (fk >> 1);
             const int di = (fi & 1) ? 1 : -1, dj = (fj & 1) ? 1 : -1, ako = (fk & 1) ? akc + 1 : akc - 1;
@@ -901,15 +1012,45 @@ k_vcycle_tail(TailArgs a)
             const long long f = (long long)(NH + fk) * g.sk + (long long)(NH + fj) * g.sj + (NH + fi);
             F.x[f] = F.x[f] + cf * (3 * pb + po);
         }
-        __syncthreads();
-        tail_fill(F.x, g, stage);                        // operators.f90:242
-        smooth(F);
+        tf.sync();
+        tail_fill(F.x, F, stage, tf);                    // operators.f90:242
+        smooth(F, tf);
     }
     // the fused legs of the finer levels rely on y == x on the wall halos of every level
+    const TailTeam& te = nwide > 0 ? wide : narrow;
+    if (!te.on) return;
     for (int l = 0; l < a.n; l++) {
         const TailLevel& L = a.lev[l];
         const long long n = L.g.sk * L.g.nz;
-        for (long long t = threadIdx.x; t < n; t += TAIL_THREADS) L.y[t] = L.x[t];
+        for (long long t = te.t; t < n; t += te.T) L.y[t] = L.x[t];
+    }
+    if (a.norm_partial) {                                // the tail is the whole cycle: sum r^2 for the stop test
+        const TailLevel& L = a.lev[0];                   // (operators.f90:81-125; x is final and fenced: the smoothing
+        double acc = 0.0;                                //  that wrote it ended with the team's barrier)
+        const int ncells = L.g.nx * L.g.ny * (L.g.nz - 2 * NH);
+        for (int t = te.t; t < ncells; t += te.T) {
+            const TailCell it(t, L.g.nx, L.g.ny, L.fx[0], L.fy[0]);
+            const double rv = tail_resid(L.x, L.b, L.g, NH + it.i, NH + it.j, NH + it.k);
+            acc = acc + rv * rv;
+        }
+        for (int o = 16; o > 0; o >>= 1) acc = acc + __shfl_xor_sync(0xffffffffu, acc, o);
+        __syncthreads();                                 // `stage` may still be in use by a halo section
+        if ((threadIdx.x & 31) == 0) stage[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int w = 0; w < TAIL_THREADS / 32; w++) t = t + stage[w];
+            a.norm_partial[blockIdx.x] = t;
+        }
+        te.sync();
+        if (blockIdx.x == 0 && threadIdx.x == 0) {       // the CTAs' partial sums in CTA order
+            double t = 0.0;
+            const int nb = nwide > 0 ? (int)gridDim.x : 1;
+            for (int w = 0; w < nb; w++) t = t + a.norm_partial[w];
+            *a.norm_out = t;
+            *a.norm_host = t;
+            __threadfence_system();
+        }
     }
 }
 
@@ -1456,20 +1597,25 @@ int up_leg(ny_mg* mg, cudaStream_t st, int lev, bool with_norm, int* nparts)
 
 // first level (1-based) of the V-cycle tail that k_vcycle_tail runs, or nlevels + 1 when there is none:
 // box on analytic coefficients (closed or periodic), levels replicated on every rank, at most tail_cells cells each
+// (narrow levels, one CTA) or, above those, at most wide_cells cells (wide levels, the whole co-resident grid)
+inline long long level_cells(const Level& L) { return (long long)L.nx * L.ny * (L.nz - 2 * NH); }
+
 int tail_first(const ny_mg* mg)
 {
     const int none = mg->nlevels + 1;
-    if (!mg->box || !mg->fused || !mg->tail) return none;
+    if (!mg->box || !mg->fused || !mg->tail || mg->tail_cells <= 0) return none;
+    const long long wide = mg->wide_max_blocks > 0 ? mg->wide_cells : 0;
     int lt = mg->nlevels;
     while (lt >= 1) {
         const Level& L = mg->lev[lt - 1];
         // replicated levels only (their z ends are walls or a local periodic wrap, never a slab neighbour)
         if (!L.gathered || L.zlo != mg->zper || L.zhi != mg->zper) break;
-        if ((long long)L.nx * L.ny * (L.nz - 2 * NH) > mg->tail_cells) break;
-        // tiny periodic levels stage their self-overlapping halo sections through shared memory
+        const bool narrow = level_cells(L) <= mg->tail_cells;
+        if (!narrow && level_cells(L) > wide) break;
+        // tiny periodic levels stage their self-overlapping halo sections through the shared memory of one CTA
         const bool wz = mg->zper;
         const bool simple = (!mg->xper || L.nx >= NH) && (!mg->yper || L.ny >= NH) && (!wz || L.nz - 2 * NH >= NH);
-        if (!simple && L.n > (size_t)TAIL_STAGE) break;
+        if (!simple && (!narrow || L.n > (size_t)TAIL_STAGE)) break;
         lt--;
     }
     lt++;
@@ -1478,23 +1624,53 @@ int tail_first(const ny_mg* mg)
     return lt;
 }
 
-int vcycle_tail(ny_mg* mg, cudaStream_t st, int lt)
+// norm_parts != nullptr and the tail starts at level 1: it also leaves sum r^2 of level 1 as *norm_parts partial sums
+int vcycle_tail(ny_mg* mg, cudaStream_t st, int lt, int* norm_parts)
 {
     TailArgs a;
     a.n = mg->nlevels - lt + 1;
+    a.nwide = 0;
+    a.bar = mg->d_bar;
+    // (one rank: a multigrid whose first level is replicated has no other slabs to sum over)
+    a.norm_partial = norm_parts && lt == 1 && !mg->comm ? mg->d_red : nullptr;
+    a.norm_out = mg->d_red + MAX_PARTIALS + 1;
+    a.norm_host = mg->ctx->h_pinned + 1;
     a.omega = mg->omega; a.cff1 = 1.0 - mg->omega;
+    long long most = 0;
     for (int l = 0; l < a.n; l++) {
         Level& L = mg->lev[lt - 1 + l];
         a.lev[l].x = L.x; a.lev[l].y = L.y; a.lev[l].b = L.b; a.lev[l].g = box_of(mg, L);
+        const int widen[3] = {0, 2, 2 * NH};
+        for (int r = 0; r < 3; r++) {
+            a.lev[l].fx[r] = fastdiv_of(L.nx + widen[r]);
+            a.lev[l].fy[r] = fastdiv_of(L.ny + widen[r]);
+        }
+        if (level_cells(L) > mg->tail_cells) {              // level sizes fall with l: the wide levels lead
+            a.nwide = l + 1;
+            const long long ring = (long long)(L.nx + 2) * (L.ny + 2) * (L.nz - 2 * NH + 2);
+            if (ring > most) most = ring;
+        }
     }
     ny_prof_scope ps(mg->ctx, NY_PROF_MG_COARSE, st);
-    k_vcycle_tail<<<1, TAIL_THREADS, 0, st>>>(a);
-    LAUNCH_OK(mg);
+    if (a.nwide == 0) {
+        k_vcycle_tail<<<1, TAIL_THREADS, 0, st>>>(a);
+        LAUNCH_OK(mg);
+        if (a.norm_partial) *norm_parts = -1;
+        return NY_OK;
+    }
+    long long blocks = (most + TAIL_THREADS - 1) / TAIL_THREADS;
+    if (blocks > mg->wide_max_blocks) blocks = mg->wide_max_blocks;
+    if (blocks < 2) blocks = 2;
+    void* args[] = {&a};
+    NY_CUDA(cudaLaunchCooperativeKernel((const void*)k_vcycle_tail, dim3((unsigned)blocks), dim3(TAIL_THREADS), args, 0, st));
+    mg->ctx->launches++;
+    if (a.norm_partial) *norm_parts = -1;
     return NY_OK;
 }
 
 // solvers.f90:35-55.  norm_parts != nullptr: the caller wants sum r^2 of level 1 after the cycle; if the
-// last leg could provide it, *norm_parts = number of partial sums waiting in d_red, else 0.
+// last leg could provide it, *norm_parts = number of partial sums waiting in d_red; -1: the one-launch tail was the
+// whole cycle and has left the finished sum in result slot 1 and in the pinned mailbox; else 0.
 int vcycle(ny_mg* mg, cudaStream_t st, int* norm_parts = nullptr)
 {
     int lev1 = mg->nlevels - 1;
@@ -1506,7 +1682,7 @@ int vcycle(ny_mg* mg, cudaStream_t st, int* norm_parts = nullptr)
         TRY(smooth(mg, st, lev));
         TRY(residual_restriction(mg, st, lev));
     }
-    if (lt <= mg->nlevels) TRY(vcycle_tail(mg, st, lt));
+    if (lt <= mg->nlevels) TRY(vcycle_tail(mg, st, lt, norm_parts));
     else TRY(smooth(mg, st, lev1 + 1));
     for (int lev = lev1; lev >= 1; lev--) {
         if (leg_ok(mg, lev)) { TRY(up_leg(mg, st, lev, lev == 1 && norm_parts, norm_parts)); continue; }
@@ -1602,6 +1778,8 @@ int create(ny_ctx* ctx, ny_comm* comm, int nx, int ny, int nz_global, int topolo
         if (e && *e) g_overlap_cells = atoll(e);
         e = getenv("NY_MG_TAIL_CELLS");
         if (e && *e) g_tail_cells = atoll(e);
+        e = getenv("NY_MG_WIDE_CELLS");
+        if (e && *e) g_wide_cells = atoll(e);
         e = getenv("NY_MG_GATHER_CELLS");
         if (e && *e) g_gather_cells = atoll(e);
         e = getenv("NY_MG_LEG_MIN_CELLS");
@@ -1611,7 +1789,7 @@ int create(ny_ctx* ctx, ny_comm* comm, int nx, int ny, int nz_global, int topolo
     memset(mg, 0, sizeof(ny_mg));
     mg->ctx = ctx; mg->comm = P > 1 ? comm : nullptr; mg->nranks = P; mg->rank = rank;
     mg->tail_cells = g_tail_cells; mg->split_tiles_min = g_split_tiles; mg->overlap_cells = g_overlap_cells;
-    mg->leg_min_cells = g_leg_min_cells;
+    mg->leg_min_cells = g_leg_min_cells; mg->wide_cells = g_wide_cells;
     mg->nh = NH; mg->maxite = 20; mg->tol = 1e-6; mg->omega = 0.9;          // mg_types.f90:15-26
     mg->topology = topology;
     mg->xper = topology == NY_TOPO_XPERIO || topology == NY_TOPO_XYPERIO || topology == NY_TOPO_XYZPERIO;
@@ -1711,10 +1889,20 @@ int create(ny_ctx* ctx, ny_comm* comm, int nx, int ny, int nz_global, int topolo
     mg->tmp_doubles = tmp_need;
     if (cudaMalloc(&mg->tmp, tmp_need * sizeof(double)) != cudaSuccess ||
         cudaMalloc(&mg->d_red, (MAX_PARTIALS + 4) * sizeof(double)) != cudaSuccess ||
-        cudaMalloc(&mg->d_flag, sizeof(int)) != cudaSuccess) {
+        cudaMalloc(&mg->d_flag, sizeof(int)) != cudaSuccess ||
+        cudaMalloc(&mg->d_bar, 2 * sizeof(unsigned)) != cudaSuccess ||
+        cudaMemset(mg->d_bar, 0, 2 * sizeof(unsigned)) != cudaSuccess) {
         ny_set_error("ny_mg_create: cudaMalloc failed");
         ny_mg_destroy(mg);
         return NY_ERR_CUDA;
+    }
+    {   // how many CTAs of the tail kernel are resident at once: the grid barrier of its wide levels needs them all
+        int dev = 0, coop = 0, per_sm = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) == cudaSuccess && coop &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_vcycle_tail, TAIL_THREADS, 0) == cudaSuccess)
+            mg->wide_max_blocks = per_sm > 0 ? ctx->num_sms : 0;              // one CTA per SM
+        cudaGetLastError();
     }
     cudaStream_t st = 0;
     int r = NY_OK;
@@ -1749,6 +1937,7 @@ extern "C" void ny_mg_destroy(ny_mg* mg)
     if (mg->tmp) cudaFree(mg->tmp);
     if (mg->d_red) cudaFree(mg->d_red);
     if (mg->d_flag) cudaFree(mg->d_flag);
+    if (mg->d_bar) cudaFree(mg->d_bar);
     delete mg;
 }
 
@@ -1766,6 +1955,7 @@ extern "C" void ny_mg_set_gather_cells(long long cells) { g_gather_cells = cells
 extern "C" void ny_mg_set_overlap_cells(long long cells) { g_overlap_cells = cells; }
 extern "C" void ny_mg_set_split_tiles(long long tiles) { g_split_tiles = tiles; }
 extern "C" void ny_mg_set_tail_cells(long long cells) { g_tail_cells = cells; }
+extern "C" void ny_mg_set_wide_cells(long long cells) { g_wide_cells = cells; }
 
 extern "C" int ny_mg_nlevels(ny_mg* mg) { return mg ? mg->nlevels : 0; }
 extern "C" int ny_mg_is_box(ny_mg* mg) { return mg ? mg->box : 0; }
@@ -1882,13 +2072,17 @@ extern "C" int ny_mg_solve(ny_mg* mg, ny_mg_stats* stats, void* stream)
         TRY(vcycle(mg, st, last ? nullptr : &parts));
         nite++;
         if (nite >= mg->maxite) break;
-        if (parts > 0) {                                      // sum r^2 came out of the last leg of the cycle
-            ny_prof_scope ps(mg->ctx, NY_PROF_MG_NORM, st);
-            TRY(finish_sum(mg, st, parts, 1));
+        if (parts < 0) {                                      // ... finished, out of the one-launch cycle
+            NY_CUDA(cudaStreamSynchronize(st));
         } else {
-            TRY(norm_r_async(mg, st));
+            if (parts > 0) {                                  // sum r^2 came out of the last leg of the cycle
+                ny_prof_scope ps(mg->ctx, NY_PROF_MG_NORM, st);
+                TRY(finish_sum(mg, st, parts, 1));
+            } else {
+                TRY(norm_r_async(mg, st));
+            }
+            TRY(read_scalars(mg, st, 2));
         }
-        TRY(read_scalars(mg, st, 2));
         res = mg->ctx->h_pinned[1] / normb;
         if (nres < 32) hist[nres++] = res;
     }

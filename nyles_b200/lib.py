@@ -85,6 +85,7 @@ _PROTOS = {
     "ny_mg_set_overlap_cells": ([_LL], None),
     "ny_mg_set_split_tiles": ([_LL], None),
     "ny_mg_set_tail_cells": ([_LL], None),
+    "ny_mg_set_wide_cells": ([_LL], None),
     "ny_mg_is_box": ([_P], _I),
     "ny_mg_set_fast_path": ([_P, _I], _I),
     "ny_mg_set_fused_legs": ([_P, _I], _I),

@@ -182,22 +182,26 @@ def test_box_kernels_equal_generic_kernels(grid):
     assert torch.equal(xf, xs)
 
 
-@pytest.mark.parametrize("split", [1, 2])
+@pytest.mark.parametrize("split,wide", [(1, 300000), (2, 0), (1, 0), (2, 1 << 40)])
 @pytest.mark.parametrize("grid", [(128, 64, 96, 1), (64, 128, 32, 1), (96, 32, 64, 1), (64, 64, 64, 5), (128, 32, 64, 6),
                                   (16, 16, 16, 6), (8, 8, 8, 1), (256, 128, 128, 1), (128, 256, 128, 5), (128, 128, 256, 6)])
-def test_fused_legs_equal_single_operator_kernels(grid, split):
-    """The TMA-staged fused V-cycle legs (smooth+residual+restriction, prolongation+smooth[+norm]) against
-    the one-box-kernel-per-operator V-cycle, bit for bit, on grids whose tiles are ragged in every direction:
-    single V-cycles from random x (halos included) and b, then complete solves with warm starts."""
+def test_fused_legs_equal_single_operator_kernels(grid, split, wide):
+    """The TMA-staged fused V-cycle legs (smooth+residual+restriction, prolongation+smooth[+norm]) and the one-launch
+    tail of the V-cycle against the one-box-kernel-per-operator V-cycle, bit for bit, on grids whose tiles are ragged
+    in every direction: single V-cycles from random x (halos included) and b, then complete solves with warm starts.
+    wide: levels of at most that many cells run inside the tail launch as its grid-barrier ("wide") levels -- the
+    default, none (every level above 4096 cells through the fused legs), or every level of every grid."""
     from nyles_b200.mgfordriver import MG
     from nyles_b200 import lib
     nx, ny, nz, topo = grid
     # test grids are small: split wherever a wall-free tile exists (a default that multigrids copy at creation)
     lib.load().ny_mg_set_split_tiles(1)
+    lib.load().ny_mg_set_wide_cells(wide)
     try:
         fused, plain = MG(1, 1, nx, ny, nz, 3, topo), MG(1, 1, nx, ny, nz, 3, topo)
     finally:
         lib.load().ny_mg_set_split_tiles(148)
+        lib.load().ny_mg_set_wide_cells(300000)
     plain.set_fused_legs(False)
     # split 1 (default): tiles away from the x / y walls run the specialised (wall-free) kernel instance,
     # the frame around them the general one; split 2: every tile through the general instance
