@@ -258,6 +258,29 @@ k_sum_final(const double* __restrict__ partial, int nb, double* __restrict__ out
     if (threadIdx.x == 0) out[0] = sh[0];
 }
 
+// k_sum_final for gridDim.x sums at once (block s: partials [s nb, (s + 1) nb) -> out[gridDim.x - 1 - s]), each also
+// stored into the host's pinned mailbox: the two norms that open a solve, ready for the stop test after one launch
+__global__ void __launch_bounds__(256)
+k_sum_final_store(const double* __restrict__ partial, int nb, double* __restrict__ out, double* host)
+{
+    __shared__ double sh[256];
+    const double* p = partial + (long long)blockIdx.x * nb;
+    double acc = 0.0;
+    for (int t = threadIdx.x; t < nb; t += blockDim.x) acc = acc + p[t];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] = sh[threadIdx.x] + sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const int slot = gridDim.x - 1 - blockIdx.x;
+        out[slot] = sh[0];
+        host[slot] = sh[0];
+        __threadfence_system();
+    }
+}
+
 // ---- array-section copy  dst = src  (Fortran indices), optionally staged through tmp ----------
 __global__ void __launch_bounds__(256)
 k_box_copy(const double* src, double* dst, Level L, int nh,
@@ -966,20 +989,22 @@ k_vcycle_tail(TailArgs a)
         const Box& gc = C.g;
         if (tf.on) {
             smooth(F, tf);
+            // eight threads per coarse cell, one fine residual each; the first adds them in the order of
+            // frestrict_centers3d (i fastest, then j, then k).  T is a multiple of 32: the eight are lanes 8m .. 8m + 7.
             const int ncells = gc.nx * gc.ny * (gc.nz - 2 * NH);
-            for (int t = tf.t; t < ncells; t += tf.T) {
-                const TailCell it(t, gc.nx, gc.ny, C.fx[0], C.fy[0]);
+            const int lane8 = threadIdx.x & 24, sub = threadIdx.x & 7;
+            for (int t = tf.t; (t & ~31) < 8 * ncells; t += tf.T) {
+                const int cell = t >> 3;
+                const bool live = cell < ncells;
+                const TailCell it(live ? cell : 0, gc.nx, gc.ny, C.fx[0], C.fy[0]);
                 const int ic = it.i, jc = it.j, kc = it.k;
-                const int ai = NH + 2 * ic, aj = NH + 2 * jc, ak = NH + 2 * kc;
-                double r = tail_resid(F.x, F.b, g, ai, aj, ak);                     // frestrict_centers3d order
-                r = r + tail_resid(F.x, F.b, g, ai + 1, aj, ak);
-                r = r + tail_resid(F.x, F.b, g, ai, aj + 1, ak);
-                r = r + tail_resid(F.x, F.b, g, ai + 1, aj + 1, ak);
-                r = r + tail_resid(F.x, F.b, g, ai, aj, ak + 1);
-                r = r + tail_resid(F.x, F.b, g, ai + 1, aj, ak + 1);
-                r = r + tail_resid(F.x, F.b, g, ai, aj + 1, ak + 1);
-                r = r + tail_resid(F.x, F.b, g, ai + 1, aj + 1, ak + 1);
-                C.b[(long long)(NH + kc) * gc.sk + (long long)(NH + jc) * gc.sj + (NH + ic)] = 0.5 * r;
+                const int ai = NH + 2 * ic + (sub & 1), aj = NH + 2 * jc + ((sub >> 1) & 1), ak = NH + 2 * kc + (sub >> 2);
+                const double rv = live ? tail_resid(F.x, F.b, g, ai, aj, ak) : 0.0;
+                double r = rv;
+#pragma unroll
+                for (int o = 1; o < 8; o++) r = r + __shfl_sync(0xffffffffu, rv, lane8 + o);
+                if (live && sub == 0)
+                    C.b[(long long)(NH + kc) * gc.sk + (long long)(NH + jc) * gc.sj + (NH + ic)] = 0.5 * r;
             }
             const long long nc = gc.sk * gc.nz;
             for (long long t = tf.t; t < nc; t += tf.T) C.x[t] = 0.0;               // operators.f90:209
@@ -1008,7 +1033,7 @@ k_vcycle_tail(TailArgs a)
             const long long co = (long long)ako * gc.sk + (long long)ajc * gc.sj + aic;
             const double pb = 9 * C.x[cb] + 3 * C.x[cb + ox] + 3 * C.x[cb + oy] + C.x[cb + ox + oy];
             const double po = 9 * C.x[co] + 3 * C.x[co + ox] + 3 * C.x[co + oy] + C.x[co + ox + oy];
-            const double cf = pcoef_of((int)in_x(gc, aic + di) + (int)in_y(gc, ajc + dj) + (int)in_z(gc, ako));
+            const double cf = pcoef_of(tin_x(gc, aic + di) + tin_y(gc, ajc + dj) + tin_z(gc, ako));
             const long long f = (long long)(NH + fk) * g.sk + (long long)(NH + fj) * g.sj + (NH + fi);
             F.x[f] = F.x[f] + cf * (3 * pb + po);
         }
@@ -1324,7 +1349,8 @@ int finish_sum(ny_mg* mg, cudaStream_t st, int nparts, int slot, int first = 0)
 
 // sum(msk*b^2) -> slot 0 and, after residual(1), sum(msk*r^2) -> slot 1, from one pass over x and b
 // (same per-thread order and reduction trees as the two separate passes: same bits)
-int norm_b_and_r_async(ny_mg* mg, cudaStream_t st);
+// stored != nullptr: the caller accepts the results in the pinned mailbox (*stored = 1) instead of read_scalars
+int norm_b_and_r_async(ny_mg* mg, cudaStream_t st, int* stored = nullptr);
 
 // sum(msk*b^2) of level 1 -> slot 0
 int norm_b_async(ny_mg* mg, cudaStream_t st)
@@ -1365,7 +1391,7 @@ int norm_r_async(ny_mg* mg, cudaStream_t st)
     return finish_sum(mg, st, nparts, 1);
 }
 
-int norm_b_and_r_async(ny_mg* mg, cudaStream_t st)
+int norm_b_and_r_async(ny_mg* mg, cudaStream_t st, int* stored)
 {
     Level& L = mg->lev[0];
     March m = march_geom(mg, L.nx, L.ny, L.nz - 2 * mg->nh);
@@ -1376,6 +1402,13 @@ int norm_b_and_r_async(ny_mg* mg, cudaStream_t st)
     ny_prof_scope ps(mg->ctx, NY_PROF_MG_NORM, st);
     k_resid<RS_NORM2><<<m.grid, dim3(32, 8), 0, st>>>(L.x, L.b, nullptr, box_of(mg, L), m.chunk, mg->d_red);
     LAUNCH_OK(mg);
+    if (!mg->comm && stored) {                 // one rank: both sums and their way to the host in one launch
+        // (the partials of sum r^2 come first, those of sum b^2 follow: result slots 1 and 0)
+        k_sum_final_store<<<2, 256, 0, st>>>(mg->d_red, m.nparts, mg->d_red + MAX_PARTIALS, mg->ctx->h_pinned);
+        LAUNCH_OK(mg);
+        *stored = 1;
+        return NY_OK;
+    }
     TRY(finish_sum(mg, st, m.nparts, 0, m.nparts));
     return finish_sum(mg, st, m.nparts, 1);
 }
@@ -2060,8 +2093,10 @@ extern "C" int ny_mg_solve(ny_mg* mg, ny_mg_stats* stats, void* stream)
     double hist[32];
     // normb = sum(msk b^2); res = sum(msk r^2)/normb after residual(1)   (operators.f90:81-125)
     // both are enqueued before the first host read: one synchronisation instead of two
-    TRY(norm_b_and_r_async(mg, st));
-    TRY(read_scalars(mg, st, 2));
+    int stored = 0;
+    TRY(norm_b_and_r_async(mg, st, &stored));
+    if (stored) NY_CUDA(cudaStreamSynchronize(st));
+    else TRY(read_scalars(mg, st, 2));
     const double normb = mg->ctx->h_pinned[0];
     double res = normb > 0.0 ? mg->ctx->h_pinned[1] / normb : 0.0;
     hist[nres++] = res;
@@ -2073,6 +2108,13 @@ extern "C" int ny_mg_solve(ny_mg* mg, ny_mg_stats* stats, void* stream)
         nite++;
         if (nite >= mg->maxite) break;
         if (parts < 0) {                                      // ... finished, out of the one-launch cycle
+            NY_CUDA(cudaStreamSynchronize(st));
+        } else if (parts > 0 && !mg->comm) {                  // one rank: final sum and its way to the host in one launch
+            {
+                ny_prof_scope ps(mg->ctx, NY_PROF_MG_NORM, st);
+                k_sum_final_store<<<1, 256, 0, st>>>(mg->d_red, parts, mg->d_red + MAX_PARTIALS + 1, mg->ctx->h_pinned + 1);
+                LAUNCH_OK(mg);
+            }
             NY_CUDA(cudaStreamSynchronize(st));
         } else {
             if (parts > 0) {                                  // sum r^2 came out of the last leg of the cycle
