@@ -18,7 +18,7 @@ timeout 700 ncu --set full --clock-control none --import-source on \
 python tools/ncu_traffic.py gpurun_out/ncu_traffic.json 134217728 gpurun_out/${TAG}_full_rhs.ncu-rep gpurun_out/${TAG}_full_mg.ncu-rep > gpurun_out/${TAG}_ncu_traffic.log 2>&1
 python bench.py > gpurun_out/${TAG}_bench_n1.json 2> gpurun_out/${TAG}_bench_n1.err
 python tools/show_bench.py gpurun_out/${TAG}_bench_n1.json | head -16
-python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${TAG}_bench_ref.json 2> gpurun_out/${TAG}_bench_ref.err
+[ -n "$SKIP_REF" ] || python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${TAG}_bench_ref.json 2> gpurun_out/${TAG}_bench_ref.err
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu --e2e-steps 1 > gpurun_out/${TAG}_ncu_launches.log 2>&1
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_smoke.log 2>&1; tail -1 gpurun_out/${TAG}_smoke.log
