@@ -232,7 +232,12 @@ int  ny_comm_stats(ny_comm* comm, long long* exchanges, long long* bytes_sent, i
 int  ny_comm_allreduce_host(ny_comm* comm, double* values_host, int n, int op_max, void* stream);
 /* Halo.fill for z slabs (core/mpi/halo.py:140-178): exchange the nh-plane z faces of `nfields`
  * arrays (fields_host: HOST array of device pointers) with ranks `below` / `above` (-1 = wall or
- * none), then wrap periodic x / y halos locally over all planes. */
+ * none), then wrap periodic x / y halos locally over all planes.
+ * COLLECTIVE, like an MPI halo exchange: every rank of `comm` must issue the same sequence of exchanges (this call,
+ * the projections and every multigrid operation on a slab multigrid) in the same order.  The peer-memory path keeps
+ * a sequence number per communicator and writes into one of a few rotating slots of the neighbour without waiting
+ * for an acknowledgement; a rank that skips an exchange leaves its neighbours spinning until their 60 s watchdog
+ * traps ("halo exchange N timed out").  Exchanges of one communicator must not be issued from two streams at once. */
 int  ny_halo_exchange(ny_ctx* ctx, ny_comm* comm, double* const* fields_host, int nfields, ny_ext e, int nh,
                       int below, int above, int yper, int xper, void* stream);
 
