@@ -261,6 +261,18 @@ def test_ncu_facts_are_stamped_with_the_kernel_sources():
     assert facts["stale"] == (facts.get("stamp") != stamp)
 
 
+def test_committed_ncu_facts_were_captured_from_these_kernel_sources():
+    """The roofline line quotes profiles/ncu_traffic.json only when its stamp is the hash of nyles_b200/csrc as it
+    stands: a kernel edit without a fresh ncu capture (tools/gpu_round.sh) turns this test red before it ships."""
+    import json
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from ncu_traffic import source_stamp
+    d = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    assert d["stamp"] == source_stamp()
+    assert d["families"]["rhs_momentum"] > 0 and d["fp64"]["rhs_momentum"]["dp_instr_per_cell"] > 0
+
+
 def test_selfcheck_cases_cover_the_three_topologies():
     from nyles_b200 import selfcheck
     for world in (2, 4, 8):
