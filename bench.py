@@ -434,7 +434,7 @@ def run_ours(args):
     for h, d in zip(host, ny.prognostic_tensors()):
         h.copy_(d)
     barrier()
-    e2_steps = max(1, min(args.steps, args.e2e_steps))
+    e2_steps = max(1, args.e2e_steps)                       # its own count: 10 by default, whatever --steps says
     t = ny.step_host(t, host) + t                          # warm the pinned path once
     barrier()
     e0.record()
